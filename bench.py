@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""MSDeformAttn hot-path benchmark (driver contract: one JSON line on stdout from rank 0).
+
+  python bench.py --gpus N --steps K --warmup W            # the sm_100a kernels
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Metric (BASELINE.json): sampled-points/s of MSDeformAttn forward+backward, point = one
+(b,q,h,l,p) sample.  Workload at any N: BASELINE configs[1] per GPU -- the DINO-R50 deformable
+encoder's self-attention, 6 layers, batch 8 @ 800x1333 (levels 100x167, 50x84, 25x42, 13x21,
+Q = S = 22223, 8 heads x 32 channels, 4 points), fp32.  One STEP = the core op's forward and
+backward for all 6 layers (6 distinct input sets, ~1.3 GB each, so nothing survives in the 126 MB
+L2 between uses).  N > 1 shards by image batch (weak scaling, 8 images per GPU, no collective
+inside the op) and adds the training config's NCCL all-reduce of the 6 modules' projection-weight
+gradients per step.
+
+  value     points/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       the same through the public autograd API with HOST buffers: pinned host -> device copies
+            of value / locations / weights / grad_output and device -> host copies of the output
+            and the three gradients inside the timed region
+  roofline  dominant kernel (backward): algorithmic bytes per launch / its mean CUDA-event
+            duration, against MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s)
+  cpu_baseline  oracle/msda_torch (the reference's grid_sample formulation) on the host cores,
+            bounded sample (one encoder layer at B=1), rank 0 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from ir_ads_b200.workloads import WORKLOADS, make_workload_inputs  # noqa: E402
+
+NUM_LAYERS = 6
+METRIC = "msda_fwd_bwd_sampled_points_per_s"
+UNIT = "points/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--dist", default="model", choices=["model", "test", "edge"])
+    ap.add_argument("--layers", type=int, default=NUM_LAYERS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="extra MSDA_FLAG_* bits (experiments)")
+    return ap.parse_args()
+
+
+def config_dict(wl, args, extra=None):
+    cfg = {
+        "workload": f"{wl.name}: DINO-R50 deformable encoder self-attn core op fwd+bwd, {args.layers} layers"
+        if wl.name == "cfg2" else f"{wl.name} core op fwd+bwd, {args.layers} layers",
+        "levels": [list(x) for x in wl.levels], "batch_per_gpu": wl.batch, "num_query": wl.queries,
+        "heads": wl.num_heads, "head_dim": wl.head_dim, "points": wl.num_points, "value_dtype": wl.value_dtype,
+        "points_per_step_per_gpu": wl.points * args.layers, "dist": args.dist,
+        "l2_hygiene": "inputs larger than L2: 6 distinct layer input sets (~1.3 GB each) cycled per step",
+        "parallelism": f"image-batch sharding x{args.gpus}, no collective inside the op",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling (NVML; nvidia-smi fallback)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting",
+               0x10: "sync_boost"}
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._nvml is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline (oracle port): rank 0 only, bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_baseline(wl, dist, iters=3, budget_s=25.0):
+    from oracle import msda_torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    value, shapes, lsi, loc, w = make_workload_inputs(wl, dist, seed=0, device="cpu", batch=1)
+    value = value.float()
+    go = torch.randn(1, wl.queries, wl.num_heads * wl.head_dim)
+    pts = wl.points // wl.batch
+    msda_torch.forward_backward(value, shapes, loc, w, go)          # warm-up
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        msda_torch.forward_backward(value, shapes, loc, w, go)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    t = statistics.median(times)
+    return {"value": pts / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"one layer of {wl.name} at batch 1 ({pts} points), fwd + autograd bwd, fp32, "
+                      f"median of {len(times)} after 1 warm-up, {t * 1e3:.0f} ms each"}
+
+
+def run_reference_arm(args, wl):
+    """--impl reference: the reference's CPU path (oracle port of multi_scale_deformable_attn_pytorch)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import msda_torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    value, shapes, lsi, loc, w = make_workload_inputs(wl, args.dist, seed=0, device="cpu", batch=1)
+    value = value.float()
+    Q = wl.queries
+    go = torch.randn(1, Q, wl.num_heads * wl.head_dim)
+    t0 = time.perf_counter()
+    msda_torch.forward_backward(value, shapes, loc, w, go)
+    probe = time.perf_counter() - t0
+    # bounded sample: keep the whole run (warm-up + steps) under ~3 minutes by taking a query prefix
+    total_iters = args.steps + args.warmup
+    frac = min(1.0, 170.0 / max(probe * total_iters, 1e-9))
+    q_used = max(64, int(Q * frac))
+    loc, w, go = loc[:, :q_used].contiguous(), w[:, :q_used].contiguous(), go[:, :q_used].contiguous()
+    pts = q_used * wl.num_heads * wl.num_levels * wl.num_points
+    for _ in range(args.warmup):
+        msda_torch.forward_backward(value, shapes, loc, w, go)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        msda_torch.forward_backward(value, shapes, loc, w, go)
+    dt = time.perf_counter() - t0
+    val = pts * args.steps / dt
+    sample = (f"one layer of {wl.name} at batch 1, first {q_used} of {Q} queries ({pts} points per step), "
+              f"fwd + autograd bwd, fp32, torch {torch.__version__}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(wl, args, {"reference_sample": sample}),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# the B200 arm
+# --------------------------------------------------------------------------------------------
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    args = parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import ir_ads_b200
+    from ir_ads_b200 import _lib, functional
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = args.layers
+    n_pts_layer = wl.points
+    fwd_bytes, bwd_bytes = wl.algorithmic_bytes()
+    out_dt = torch.bfloat16 if wl.value_dtype == "bf16" else torch.float32
+    if wl.deterministic:
+        functional.set_deterministic(True)
+
+    layers = []
+    for i in range(L):
+        value, shapes, lsi, loc, w = make_workload_inputs(wl, args.dist, seed=100 * rank + i, device=dev)
+        go = torch.randn(wl.batch, wl.queries, wl.num_heads * wl.head_dim, device=dev,
+                         generator=torch.Generator(device=dev).manual_seed(7 + i)).to(out_dt)
+        layers.append((value, shapes, lsi, loc, w, go))
+    # the training config's all-reduce payload: projection-weight grads of the L modules
+    proj_grads = torch.zeros(L * 230272, device=dev) if dist_on else None
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(record=None):
+        for i, (value, shapes, lsi, loc, w, go) in enumerate(layers):
+            if record is not None:
+                e0, e1, e2 = ev(), ev(), ev()
+                e0.record()
+            out = ir_ads_b200.ms_deform_attn_forward(value, shapes, lsi, loc, w, 64)
+            if record is not None:
+                e1.record()
+            ir_ads_b200.ms_deform_attn_backward(value, shapes, lsi, loc, w, go, 64)
+            if record is not None:
+                e2.record()
+                record.append((e0, e1, e2))
+            del out
+        if dist_on:
+            dist.all_reduce(proj_grads)
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with functional.kernel_flags(args.flags):
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = _lib.launch_count()
+        t_begin, t_end = ev(), ev()
+        t_begin.record()
+        for _ in range(args.steps):
+            step()
+        t_end.record()
+        barrier()
+        launches = _lib.launch_count() - launches0
+        clocks = sampler.stop()
+        ms_total = t_begin.elapsed_time(t_end)
+
+        # per-kernel durations (same stream, separate short pass so event records do not perturb `value`)
+        recs = []
+        for _ in range(3):
+            step(recs)
+        torch.cuda.synchronize()
+        fwd_ms = statistics.mean(a.elapsed_time(b) for a, b, _ in recs)
+        bwd_ms = statistics.mean(b.elapsed_time(c) for _, b, c in recs)
+
+    ms_step = ms_total / args.steps
+    if dist_on:
+        t = torch.tensor([ms_step], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    value_pts = n_pts_layer * L * world / (ms_step * 1e-3)
+
+    # ---------------- e2e: public autograd API, host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        with functional.kernel_flags(args.flags):
+            e2e = run_e2e(wl, layers, dev, dist_on, world, args)
+
+    ref_cuda = None
+    if rank == 0 and not args.no_ref_cuda and wl.value_dtype == "f32":
+        ref_cuda = run_ref_cuda(layers[:3], n_pts_layer)
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value_pts, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if wl.value_dtype == "f32" else "bf16(value) + f32 accumulate",
+            "data": "synthetic", "config": config_dict(wl, args),
+            "roofline": {"bound": "hbm", "kernel": _lib.lib().msda_dispatch_name(
+                wl.head_dim, wl.num_levels, wl.num_points, wl.spatial_size, wl.num_heads,
+                _lib.MSDA_BF16 if wl.value_dtype == "bf16" else _lib.MSDA_F32, args.flags, 1).decode(),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
+                "launch_ms": bwd_ms, "note": "launch_ms includes the grad_value zero-fill memset issued by msda_backward",
+                "fwd": {"algorithmic_bytes_per_launch": fwd_bytes, "launch_ms": fwd_ms,
+                        "achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "frac": fwd_bytes / (fwd_ms * 1e-3) / 1e9 / peak},
+                "fwd_bwd_frac": (fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if ref_cuda is not None:
+            line["reference_cuda_same_gpu"] = ref_cuda
+        if not args.no_cpu_baseline and world >= 1:
+            line["cpu_baseline"] = cpu_baseline(wl, args.dist)
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(wl, layers, dev, dist_on, world, args):
+    """Host buffers in, host buffers out, through MultiScaleDeformableAttnFunction.apply + backward."""
+    import ir_ads_b200
+    value, shapes, lsi, loc, w, go = layers[0]
+    host_in = [t.cpu().pin_memory() for t in (value, loc, w, go)]
+    out_shape = (wl.batch, wl.queries, wl.num_heads * wl.head_dim)
+    host_out = [torch.empty(out_shape, dtype=value.dtype).pin_memory(), torch.empty_like(host_in[0]).pin_memory(),
+                torch.empty_like(host_in[1]).pin_memory(), torch.empty_like(host_in[2]).pin_memory()]
+    h2d = sum(t.numel() * t.element_size() for t in host_in)
+    d2h = sum(t.numel() * t.element_size() for t in host_out)
+    L = len(layers)
+    steps = max(2, min(args.steps, 5))
+
+    def one_layer():
+        v = host_in[0].to(dev, non_blocking=True).requires_grad_(True)
+        lo = host_in[1].to(dev, non_blocking=True).requires_grad_(True)
+        ww = host_in[2].to(dev, non_blocking=True).requires_grad_(True)
+        g = host_in[3].to(dev, non_blocking=True)
+        out = ir_ads_b200.MultiScaleDeformableAttnFunction.apply(v, shapes, lsi, lo, ww, 64)
+        out.backward(g)
+        host_out[0].copy_(out.detach(), non_blocking=True)
+        host_out[1].copy_(v.grad, non_blocking=True)
+        host_out[2].copy_(lo.grad, non_blocking=True)
+        host_out[3].copy_(ww.grad, non_blocking=True)
+
+    for _ in range(2):
+        one_layer()
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        for _ in range(L):
+            one_layer()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    if dist_on:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": wl.points * L * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * L,
+            "d2h_bytes_per_step": d2h * L, "ms_per_step": ms, "steps": steps,
+            "path": "pinned host -> H2D -> MultiScaleDeformableAttnFunction.apply + backward -> D2H of out and 3 grads"}
+
+
+def run_ref_cuda(layers, n_pts_layer):
+    """The reference's own kernels (oracle/_ref, unmodified, sm_100a) on the same inputs and GPU."""
+    try:
+        from oracle import ref_cuda
+        if not ref_cuda.available():
+            return None
+        bufs = None
+        times_f, times_b = [], []
+        for it in range(3):
+            for value, shapes, lsi, loc, w, go in layers:
+                if bufs is None:
+                    bufs = (torch.empty_like(value), torch.empty_like(loc), torch.empty_like(w))
+                    out = torch.empty_like(go)
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+                out.zero_()
+                ref_cuda.forward(value, shapes, lsi, loc, w, out)
+                e1.record()
+                ref_cuda.backward(go, value, shapes, lsi, loc, w, bufs)
+                e2.record()
+                torch.cuda.synchronize()
+                if it > 0:
+                    times_f.append(e0.elapsed_time(e1))
+                    times_b.append(e1.elapsed_time(e2))
+        f, b = statistics.mean(times_f), statistics.mean(times_b)
+        return {"value": n_pts_layer / ((f + b) * 1e-3), "unit": UNIT, "fwd_ms": f, "bwd_ms": b,
+                "what": "reference ms_deformable_im2col/col2im kernels compiled for sm_100a, incl. its zero-fills"}
+    except Exception as exc:  # a baseline must never take the bench down
+        return {"error": repr(exc)}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+/*
+ * msda.h -- C ABI of the B200-native multi-scale deformable attention library (libmsda_b200.so).
+ *
+ * This is the drop-in boundary for the reference's native MSDeformAttn pair.  A maintainer of
+ * the reference binds these entry points where detrex binds its own kernels today
+ * (INTEGRATION.md shows the ctypes / pybind stub):
+ *
+ *   msda_forward   replaces  ms_deformable_im2col_cuda<T>
+ *                  (/root/reference/detrex/layers/csrc/MsDeformAttn/ms_deform_im2col_cuda.cuh:923-954),
+ *                  i.e. the body of ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:21-81),
+ *                  exported to Python as detrex._C.ms_deform_attn_forward (csrc/vision.cpp:55).
+ *   msda_backward  replaces  ms_deformable_col2im_cuda<T> (ms_deform_im2col_cuda.cuh:956-1327),
+ *                  i.e. the body of ms_deform_attn_cuda_backward (ms_deform_attn_cuda.cu:84-154),
+ *                  exported as detrex._C.ms_deform_attn_backward (csrc/vision.cpp:56).
+ *
+ * Argument order and meaning follow those two launchers: stream first, then the tensors, then
+ * (batch, spatial_size, num_heads, channels, num_levels, num_query, num_point), then outputs.
+ * Differences, all deliberate:
+ *   - plain C: no ATen / torch types, `void*` for the stream (a cudaStream_t);
+ *   - a dtype tag instead of a C++ template: float, double, or bfloat16 value with float
+ *     locations / weights (the reference has float and double only);
+ *   - errors are RETURNED (the reference only printf's launch failures, cuh:948-952);
+ *   - no im2col_step: the whole batch is one launch (ms_deform_attn_cuda.cu:51-76 chunked it);
+ *   - backward takes a caller-owned workspace (size from msda_backward_workspace_bytes) because
+ *     the library never allocates device memory.
+ *
+ * Tensor layouts (all contiguous, all device pointers, as the reference asserts
+ * ms_deform_attn_cuda.cu:29-39):
+ *   value              [B, S, H, D]        dtype
+ *   spatial_shapes     [L, 2]  int64  (H_l, W_l)
+ *   level_start_index  [L]     int64
+ *   sampling_loc       [B, Q, H, L, P, 2]  (x, y) normalised to [0,1] over the level; float
+ *                                          (double when dtype == MSDA_F64)
+ *   attn_weight        [B, Q, H, L, P]     same type as sampling_loc
+ *   output / grad_output        [B, Q, H*D]   dtype
+ *   grad_value         [B, S, H, D]        dtype        (zero-filled by the library)
+ *   grad_sampling_loc, grad_attn_weight    shaped/typed like sampling_loc / attn_weight
+ *                                          (fully written by the library, no pre-zeroing needed)
+ *
+ * Thread safety: re-entrant, no global mutable state except a launch counter and a
+ * thread-local last-error string.  Work is enqueued on `stream` of the device that owns `value`
+ * (the library switches to that device for the call and restores the previous one).
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+/* dtype tags */
+#define MSDA_F32 0  /* value/out/grads float,  loc/w float  */
+#define MSDA_F64 1  /* everything double (gradcheck path; generic kernels only) */
+#define MSDA_BF16 2 /* value/out/grad_out/grad_value bfloat16, loc/w and their grads float, fp32 accumulate */
+
+/* status codes */
+#define MSDA_OK 0
+#define MSDA_ERR_INVALID_ARGUMENT 1 /* null pointer, negative size, unknown dtype ...            */
+#define MSDA_ERR_UNSUPPORTED 2      /* shape outside what any kernel handles                     */
+#define MSDA_ERR_WORKSPACE 3        /* workspace missing or smaller than msda_backward_workspace_bytes */
+#define MSDA_ERR_CUDA 4             /* a CUDA runtime call or kernel launch failed; see msda_last_error_message */
+
+/* flags (bit set) */
+#define MSDA_FLAG_DETERMINISTIC (1u << 0) /* backward: bit-reproducible grad_value (no float atomics) */
+#define MSDA_FLAG_FORCE_GENERIC (1u << 1) /* bypass the D in {16,32,64,128} fast kernels             */
+#define MSDA_FLAG_ORDER_LINEAR (1u << 2)  /* rows processed in memory order (no locality re-ordering) */
+
+int msda_abi_version(void);
+
+/* Forward.  Returns MSDA_OK or an error code.  B*Q*H*D == 0 is a no-op. */
+int msda_forward(void* stream, const void* value, const int64_t* spatial_shapes,
+                 const int64_t* level_start_index, const void* sampling_loc, const void* attn_weight,
+                 int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                 int num_query, int num_point, void* output, int dtype, unsigned flags);
+
+/* Bytes of device scratch msda_backward needs for this problem (0 is possible). */
+size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
+                                     int num_levels, int num_query, int num_point, int dtype,
+                                     unsigned flags);
+
+/* Backward: the three gradients of the forward above w.r.t. value, sampling_loc, attn_weight. */
+int msda_backward(void* stream, const void* grad_output, const void* value,
+                  const int64_t* spatial_shapes, const int64_t* level_start_index,
+                  const void* sampling_loc, const void* attn_weight, int batch, int spatial_size,
+                  int num_heads, int channels, int num_levels, int num_query, int num_point,
+                  void* grad_value, void* grad_sampling_loc, void* grad_attn_weight,
+                  void* workspace, size_t workspace_bytes, int dtype, unsigned flags);
+
+/*
+ * Test hook: the integer bookkeeping the float kernels derive from every sampling point.
+ *   corner_offsets [B*Q*H*L*P, 4] int64  flat element offset (channel 0) of the four bilinear
+ *                  corners inside `value`, -1 for a zero-padded corner or a gated-out point;
+ *   frac           [B*Q*H*L*P, 2] float  (lw, lh) fractional weights.
+ * Same definition as msda_oracle_bookkeeping in oracle/msda_oracle.c; compared bit for bit.
+ */
+int msda_debug_bookkeeping(void* stream, const float* sampling_loc, const int64_t* spatial_shapes,
+                           const int64_t* level_start_index, int batch, int spatial_size,
+                           int num_heads, int channels, int num_levels, int num_query,
+                           int num_point, int64_t* corner_offsets, float* frac);
+
+/* Human-readable name of a status code. */
+const char* msda_status_string(int status);
+/* Detail of the last failure on the calling thread ("" if none). */
+const char* msda_last_error_message(void);
+/* Number of kernels this library has launched in this process (monotonic). */
+uint64_t msda_kernel_launch_count(void);
+/* Name of the kernel family the given problem dispatches to ("fast_d32_f32", "generic_f64", ...). */
+const char* msda_dispatch_name(int channels, int num_levels, int num_point, int spatial_size,
+                               int num_heads, int dtype, unsigned flags, int backward);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

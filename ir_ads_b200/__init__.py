@@ -1,0 +1,24 @@
+"""B200-native multi-scale deformable attention -- drop-in for the MSDeformAttn hot path of
+yunduo-vision/IR-ADS (detrex.layers.MultiScaleDeformableAttention and the
+ms_deform_attn_forward / backward CUDA pair).  See DESIGN.md and include/msda.h.
+
+Importing the package does not load the CUDA library; the first op call does, and fails loudly
+if ir_ads_b200/libmsda_b200.so has not been built (no CPU / PyTorch fallback exists).
+"""
+from .functional import (  # noqa: F401
+    MultiScaleDeformableAttnFunction,
+    kernel_flags,
+    ms_deform_attn_backward,
+    ms_deform_attn_forward,
+    set_deterministic,
+)
+from .module import MultiScaleDeformableAttention  # noqa: F401
+
+__all__ = [
+    "MultiScaleDeformableAttention",
+    "MultiScaleDeformableAttnFunction",
+    "ms_deform_attn_forward",
+    "ms_deform_attn_backward",
+    "set_deterministic",
+    "kernel_flags",
+]

@@ -1,0 +1,376 @@
+// msda_capi.cu -- host side of libmsda_b200.so: argument checks, kernel selection, launches.
+// The C ABI is declared and documented in include/msda.h.
+//
+// Plays the role of ms_deform_attn_cuda_forward / _backward
+// (/root/reference/detrex/layers/csrc/MsDeformAttn/ms_deform_attn_cuda.cu:21-154) and of the
+// kernel selector ms_deformable_col2im_cuda (ms_deform_im2col_cuda.cuh:956-1327), minus ATen:
+// no allocation, no im2col_step chunk loop (one launch covers the batch), errors returned.
+#include "../../include/msda.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "msda_fast.cuh"
+#include "msda_generic.cuh"
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+thread_local char g_err[512] = "";
+
+int fail(int status, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(MSDA_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define MSDA_CUDA(call)                                   \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+// Runs the call on the device that owns `ptr`, restoring the caller's device afterwards
+// (the reference has no guard at all: ms_deform_attn_cuda.cu:66 just takes the current stream).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(const void* ptr) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+    if (e != cudaSuccess) return e;
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) return cudaErrorInvalidDevicePointer;
+    e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (attr.device != prev) {
+      e = cudaSetDevice(attr.device);
+      switched = (e == cudaSuccess);
+    }
+    return e;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+struct Dims {
+  int B, S, H, D, L, Q, P;
+  int64_t rows() const { return (int64_t)B * Q * H; }
+  int64_t n_value() const { return (int64_t)B * S * H * D; }
+  int64_t n_points() const { return rows() * L * P; }
+};
+
+int check_dims(const Dims& d, int dtype) {
+  if (d.B < 0 || d.S < 0 || d.H < 0 || d.D < 0 || d.L < 0 || d.Q < 0 || d.P < 0)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "negative dimension (B=%d S=%d H=%d D=%d L=%d Q=%d P=%d)", d.B, d.S, d.H,
+                d.D, d.L, d.Q, d.P);
+  if (dtype != MSDA_F32 && dtype != MSDA_F64 && dtype != MSDA_BF16)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "unknown dtype tag %d", dtype);
+  return MSDA_OK;
+}
+
+bool fast_ok(const Dims& d, int dtype, unsigned flags) {
+  if (flags & MSDA_FLAG_FORCE_GENERIC) return false;
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
+  if (!(d.D == 16 || d.D == 32 || d.D == 64 || d.D == 128)) return false;
+  if (d.L < 1 || d.L > msda::kFastMaxLevels) return false;
+  if (d.L * d.P < 1 || d.L * d.P > msda::kFastMaxPoints) return false;
+  // element offsets inside one image are 32-bit in the fast kernels (one spare row/pixel of slack)
+  if (((int64_t)d.S + 65536) * d.H * d.D >= ((int64_t)1 << 31)) return false;
+  return true;
+}
+
+int grid_for(int64_t work_items, int threads, int cap_blocks) {
+  int64_t g = (work_items + threads - 1) / threads;
+  if (g > cap_blocks) g = cap_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------
+// fast-kernel launch helpers
+// ------------------------------------------------------------------------------------------
+template <typename K>
+cudaError_t ensure_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+template <int D, typename VT, int PT>
+int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
+                    const void* loc, const void* w, void* out) {
+  constexpr int RPC = (msda::kFastThreads / 32) * (32 / (D / 4));
+  const int NP = d.L * d.P;
+  const size_t smem = sizeof(msda::LevelTab) + (size_t)RPC * ((((NP * 5 + 3) & ~3) + 4) * 4);
+  auto k = msda::msda_fwd_fast_kernel<D, VT, PT>;
+  MSDA_CUDA(ensure_smem(k, smem));
+  const int64_t rows = d.rows();
+  const unsigned grid = (unsigned)((rows + RPC - 1) / RPC);
+  k<<<grid, msda::kFastThreads, smem, st>>>((const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
+                                            (VT*)out, d.S, d.H, d.L, d.Q, d.P, rows);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MSDA_CUDA(cudaGetLastError());
+  return MSDA_OK;
+}
+
+template <int D, typename VT, int PT>
+int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
+                    const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl, void* gw) {
+  constexpr int RPC = (msda::kFastThreads / 32) * (32 / (D / 4));
+  const int NP = d.L * d.P;
+  const size_t smem = sizeof(msda::LevelTab) + (size_t)RPC * (NP + 1) * 16;
+  auto k = msda::msda_bwd_fast_kernel<D, VT, PT>;
+  MSDA_CUDA(ensure_smem(k, smem));
+  const int64_t rows = d.rows();
+  const unsigned grid = (unsigned)((rows + RPC - 1) / RPC);
+  k<<<grid, msda::kFastThreads, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc,
+                                            (const float*)w, gv, (float*)gl, (float*)gw, d.S, d.H, d.L, d.Q, d.P,
+                                            rows);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MSDA_CUDA(cudaGetLastError());
+  return MSDA_OK;
+}
+
+#define MSDA_DISPATCH_PT(D_, VT_, CALL)                      \
+  do {                                                       \
+    if (d.P == 4) { constexpr int PT_ = 4; return CALL(D_, VT_, PT_); } \
+    if (d.P == 8) { constexpr int PT_ = 8; return CALL(D_, VT_, PT_); } \
+    { constexpr int PT_ = 0; return CALL(D_, VT_, PT_); }    \
+  } while (0)
+
+#define MSDA_DISPATCH_D(VT_, CALL)                           \
+  do {                                                       \
+    switch (d.D) {                                           \
+      case 16: MSDA_DISPATCH_PT(16, VT_, CALL);              \
+      case 32: MSDA_DISPATCH_PT(32, VT_, CALL);              \
+      case 64: MSDA_DISPATCH_PT(64, VT_, CALL);              \
+      case 128: MSDA_DISPATCH_PT(128, VT_, CALL);            \
+      default: return fail(MSDA_ERR_UNSUPPORTED, "fast path: D=%d", d.D); \
+    }                                                        \
+  } while (0)
+
+int fwd_fast(cudaStream_t st, const Dims& d, int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
+             const void* loc, const void* w, void* out) {
+#define CALL_FWD(D_, VT_, PT_) launch_fwd_fast<D_, VT_, PT_>(st, d, value, shapes, lsi, loc, w, out)
+  if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_FWD);
+  MSDA_DISPATCH_D(__nv_bfloat16, CALL_FWD);
+#undef CALL_FWD
+}
+
+int bwd_fast(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
+             const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl, void* gw) {
+#define CALL_BWD(D_, VT_, PT_) launch_bwd_fast<D_, VT_, PT_>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw)
+  if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
+  MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
+#undef CALL_BWD
+}
+
+// ------------------------------------------------------------------------------------------
+// generic launches
+// ------------------------------------------------------------------------------------------
+template <typename VT, typename CT>
+int fwd_generic(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
+                const void* loc, const void* w, void* out) {
+  const int64_t total = d.rows() * d.D;
+  const int grid = grid_for(total, 256, 148 * 32);
+  msda::msda_fwd_generic_kernel<VT, CT><<<grid, 256, 0, st>>>((const VT*)value, shapes, lsi, (const CT*)loc,
+                                                              (const CT*)w, (VT*)out, d.S, d.H, d.D, d.L, d.Q, d.P,
+                                                              total);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MSDA_CUDA(cudaGetLastError());
+  return MSDA_OK;
+}
+
+template <typename VT, typename CT>
+int bwd_generic(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
+                const int64_t* lsi, const void* loc, const void* w, CT* gv, void* gl, void* gw) {
+  int threads = 32;
+  while (threads < d.D && threads < 256) threads <<= 1;
+  const int64_t rows = d.rows();
+  const int grid = (int)(rows < 148 * 64 ? rows : 148 * 64);
+  msda::msda_bwd_generic_kernel<VT, CT><<<grid, threads, 0, st>>>((const VT*)go, (const VT*)value, shapes, lsi,
+                                                                  (const CT*)loc, (const CT*)w, gv, (CT*)gl, (CT*)gw,
+                                                                  d.S, d.H, d.D, d.L, d.Q, d.P, rows);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MSDA_CUDA(cudaGetLastError());
+  return MSDA_OK;
+}
+
+size_t elem_size(int dtype) { return dtype == MSDA_F64 ? 8 : (dtype == MSDA_BF16 ? 2 : 4); }
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int msda_abi_version(void) { return MSDA_ABI_VERSION; }
+
+uint64_t msda_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* msda_last_error_message(void) { return g_err; }
+
+const char* msda_status_string(int status) {
+  switch (status) {
+    case MSDA_OK: return "MSDA_OK";
+    case MSDA_ERR_INVALID_ARGUMENT: return "MSDA_ERR_INVALID_ARGUMENT";
+    case MSDA_ERR_UNSUPPORTED: return "MSDA_ERR_UNSUPPORTED";
+    case MSDA_ERR_WORKSPACE: return "MSDA_ERR_WORKSPACE";
+    case MSDA_ERR_CUDA: return "MSDA_ERR_CUDA";
+    default: return "MSDA_ERR_UNKNOWN";
+  }
+}
+
+const char* msda_dispatch_name(int channels, int num_levels, int num_point, int spatial_size, int num_heads,
+                               int dtype, unsigned flags, int backward) {
+  Dims d{1, spatial_size, num_heads, channels, num_levels, 1, num_point};
+  static thread_local char name[64];
+  const char* dt = dtype == MSDA_F64 ? "f64" : (dtype == MSDA_BF16 ? "bf16" : "f32");
+  if (fast_ok(d, dtype, flags))
+    snprintf(name, sizeof(name), "%s_fast_d%d_%s", backward ? "bwd" : "fwd", channels, dt);
+  else
+    snprintf(name, sizeof(name), "%s_generic_%s", backward ? "bwd" : "fwd", dt);
+  return name;
+}
+
+int msda_forward(void* stream, const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                 const void* sampling_loc, const void* attn_weight, int batch, int spatial_size, int num_heads,
+                 int channels, int num_levels, int num_query, int num_point, void* output, int dtype,
+                 unsigned flags) {
+  g_err[0] = 0;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  if (int s = check_dims(d, dtype)) return s;
+  if (d.rows() * d.D == 0) return MSDA_OK;  // nothing to write (the reference would launch a 0-block grid, cuh:942)
+  if (!output) return fail(MSDA_ERR_INVALID_ARGUMENT, "output is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d.n_points() == 0 || d.S == 0) {  // no samples: the sum over an empty set
+    DeviceGuard g;
+    MSDA_CUDA(g.enter(output));
+    MSDA_CUDA(cudaMemsetAsync(output, 0, (size_t)(d.rows() * d.D) * elem_size(dtype), st));
+    return MSDA_OK;
+  }
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  DeviceGuard guard;
+  MSDA_CUDA(guard.enter(value));
+  if (fast_ok(d, dtype, flags))
+    return fwd_fast(st, d, dtype, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
+  switch (dtype) {
+    case MSDA_F32:
+      return fwd_generic<float, float>(st, d, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
+    case MSDA_F64:
+      return fwd_generic<double, double>(st, d, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
+    default:
+      return fwd_generic<__nv_bfloat16, float>(st, d, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
+  }
+}
+
+size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                                     int num_query, int num_point, int dtype, unsigned flags) {
+  (void)num_levels; (void)num_query; (void)num_point; (void)flags;
+  if (batch <= 0 || spatial_size <= 0 || num_heads <= 0 || channels <= 0) return 0;
+  // bf16 grad_value is accumulated in float and converted at the end
+  if (dtype == MSDA_BF16) return (size_t)batch * spatial_size * num_heads * channels * sizeof(float);
+  return 0;
+}
+
+int msda_backward(void* stream, const void* grad_output, const void* value, const int64_t* spatial_shapes,
+                  const int64_t* level_start_index, const void* sampling_loc, const void* attn_weight, int batch,
+                  int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                  void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
+                  size_t workspace_bytes, int dtype, unsigned flags) {
+  g_err[0] = 0;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  if (int s = check_dims(d, dtype)) return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t es = elem_size(dtype);
+  const size_t ls = dtype == MSDA_F64 ? 8 : 4;
+  if (d.n_value() == 0 && d.n_points() == 0) return MSDA_OK;
+  const void* anchor = d.n_value() ? grad_value : grad_attn_weight;
+  if (!anchor) return fail(MSDA_ERR_INVALID_ARGUMENT, "gradient output pointer is null");
+  DeviceGuard guard;
+  MSDA_CUDA(guard.enter(anchor));
+  if (d.n_value()) {
+    if (!grad_value) return fail(MSDA_ERR_INVALID_ARGUMENT, "grad_value is null");
+    MSDA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)d.n_value() * es, st));
+  }
+  if (d.n_points() == 0) return MSDA_OK;
+  if (!grad_sampling_loc || !grad_attn_weight) return fail(MSDA_ERR_INVALID_ARGUMENT, "grad_loc / grad_w is null");
+  if (d.n_value() == 0 || d.D == 0) {  // nothing to sample from: all gradients are zero
+    MSDA_CUDA(cudaMemsetAsync(grad_sampling_loc, 0, (size_t)d.n_points() * 2 * ls, st));
+    MSDA_CUDA(cudaMemsetAsync(grad_attn_weight, 0, (size_t)d.n_points() * ls, st));
+    return MSDA_OK;
+  }
+  if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  if (flags & MSDA_FLAG_DETERMINISTIC)
+    return fail(MSDA_ERR_UNSUPPORTED, "deterministic backward is not implemented in this build");
+
+  float* gv32 = static_cast<float*>(grad_value);
+  if (dtype == MSDA_BF16) {
+    const size_t need = msda_backward_workspace_bytes(batch, spatial_size, num_heads, channels, num_levels, num_query,
+                                                      num_point, dtype, flags);
+    if (!workspace || workspace_bytes < need)
+      return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, workspace_bytes);
+    gv32 = static_cast<float*>(workspace);
+    MSDA_CUDA(cudaMemsetAsync(gv32, 0, need, st));
+  }
+
+  int s;
+  if (fast_ok(d, dtype, flags)) {
+    s = bwd_fast(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, gv32,
+                 grad_sampling_loc, grad_attn_weight);
+  } else if (dtype == MSDA_F32) {
+    s = bwd_generic<float, float>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                                  attn_weight, gv32, grad_sampling_loc, grad_attn_weight);
+  } else if (dtype == MSDA_F64) {
+    s = bwd_generic<double, double>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                                    attn_weight, static_cast<double*>(grad_value), grad_sampling_loc,
+                                    grad_attn_weight);
+  } else {
+    s = bwd_generic<__nv_bfloat16, float>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                                          attn_weight, gv32, grad_sampling_loc, grad_attn_weight);
+  }
+  if (s != MSDA_OK) return s;
+  if (dtype == MSDA_BF16) {
+    const int64_t n = d.n_value();
+    msda::msda_cast_f32_to_bf16_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
+        gv32, static_cast<__nv_bfloat16*>(grad_value), n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    MSDA_CUDA(cudaGetLastError());
+  }
+  return MSDA_OK;
+}
+
+int msda_debug_bookkeeping(void* stream, const float* sampling_loc, const int64_t* spatial_shapes,
+                           const int64_t* level_start_index, int batch, int spatial_size, int num_heads, int channels,
+                           int num_levels, int num_query, int num_point, int64_t* corner_offsets, float* frac) {
+  g_err[0] = 0;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  if (int s = check_dims(d, MSDA_F32)) return s;
+  if (d.n_points() == 0) return MSDA_OK;
+  if (!sampling_loc || !spatial_shapes || !level_start_index || !corner_offsets || !frac)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  DeviceGuard guard;
+  MSDA_CUDA(guard.enter(sampling_loc));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  msda::msda_bookkeeping_kernel<<<grid_for(d.n_points(), 256, 148 * 16), 256, 0, st>>>(
+      sampling_loc, spatial_shapes, level_start_index, d.S, d.H, d.D, d.L, d.Q, d.P, d.n_points(), corner_offsets,
+      frac);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MSDA_CUDA(cudaGetLastError());
+  return MSDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// msda_coords.cuh -- where does a normalised sampling location land on a level?
+//
+// Reference semantics (/root/reference/detrex/layers/csrc/MsDeformAttn/ms_deform_im2col_cuda.cuh):
+//   :284-285  h_im = loc_h * H_l - 0.5, w_im = loc_w * W_l - 0.5
+//   :288      the point contributes only if h_im > -1 && w_im > -1 && h_im < H_l && w_im < W_l
+//   :39-46    cell = floor(), fractional weights lh, lw
+//   :56-80    each of the four corners is zero-padded individually
+//
+// Float path: the reference rounds loc*size to fp32 before it subtracts 0.5, which costs up to
+// ~4e-6 px at size ~170 and occasionally picks the neighbouring cell.  Here the rounding error of
+// the product is recovered with one fma (e = fma(loc,size,-p) is exact), so cell and fraction are
+// those of the EXACT value of loc*size-0.5 -- the same cell the fp64 grid_sample oracle picks.
+// oracle/msda_oracle.c::split_f32_compensated restates these lines operation for operation; the
+// bookkeeping test compares the two bit for bit, so keep them in lock step.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace msda {
+
+template <typename T>
+struct AxisSplit {
+  int low;     // floor(coord) (0 when !ok)
+  T frac;      // coord - low  (0 when !ok)
+  bool ok;     // coord > -1 && coord < size   (false for NaN / Inf)
+};
+
+__device__ __forceinline__ AxisSplit<float> split_axis(float loc, int size) {
+  AxisSplit<float> s;
+  const float sz = (float)size;
+  const float p = __fmul_rn(loc, sz);
+  const float e = __fmaf_rn(loc, sz, -p);
+  const float a = __fsub_rn(p, 0.5f);
+  float f0 = floorf(a);
+  const float d = __fsub_rn(__fsub_rn(p, f0), 0.5f);
+  float r = __fadd_rn(d, e);
+  if (r < 0.0f) {
+    f0 -= 1.0f;
+    r = __fadd_rn(r, 1.0f);
+  } else if (r >= 1.0f) {
+    f0 += 1.0f;
+    r = __fsub_rn(r, 1.0f);
+  }
+  s.ok = (f0 >= 0.0f || (f0 == -1.0f && r > 0.0f)) && (f0 < sz);
+  s.low = s.ok ? (int)f0 : 0;
+  s.frac = s.ok ? r : 0.0f;
+  return s;
+}
+
+__device__ __forceinline__ AxisSplit<double> split_axis(double loc, int size) {
+  AxisSplit<double> s;
+  const double c = loc * (double)size - 0.5;  // the reference expression, evaluated in double
+  s.ok = (c > -1.0) && (c < (double)size);
+  const double fl = floor(c);
+  s.low = s.ok ? (int)fl : 0;
+  s.frac = s.ok ? (c - fl) : 0.0;
+  return s;
+}
+
+// One sampling point on one level.
+template <typename T>
+struct Cell {
+  int y0, x0;       // low corner (may be -1)
+  T lh, lw;         // fractional parts
+  unsigned valid;   // bit k set <=> corner k is inside the map; 0 when the point is gated out
+                    // k: 0=(y0,x0) 1=(y0,x0+1) 2=(y0+1,x0) 3=(y0+1,x0+1)   (v1..v4 of cuh:56-80)
+};
+
+template <typename T>
+__device__ __forceinline__ Cell<T> locate(T loc_x, T loc_y, int H, int W) {
+  Cell<T> c;
+  const AxisSplit<T> ay = split_axis(loc_y, H);
+  const AxisSplit<T> ax = split_axis(loc_x, W);
+  c.y0 = ay.low;
+  c.x0 = ax.low;
+  c.lh = ay.frac;
+  c.lw = ax.frac;
+  unsigned v = 0;
+  if (ay.ok && ax.ok) {
+    const bool y0ok = c.y0 >= 0, y1ok = c.y0 + 1 <= H - 1;
+    const bool x0ok = c.x0 >= 0, x1ok = c.x0 + 1 <= W - 1;
+    v = (unsigned)(y0ok && x0ok) | ((unsigned)(y0ok && x1ok) << 1) | ((unsigned)(y1ok && x0ok) << 2) |
+        ((unsigned)(y1ok && x1ok) << 3);
+  }
+  c.valid = v;
+  return c;
+}
+
+}  // namespace msda

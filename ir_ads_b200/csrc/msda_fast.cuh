@@ -1,0 +1,328 @@
+// msda_fast.cuh -- the sm_100a MSDeformAttn kernels for head dims 16/32/64/128 (float or bf16 value).
+//
+// Work decomposition (forward and backward): a "row" is one (image b, query q, head h); its D
+// channels are covered by LANES = D/4 adjacent lanes holding 4 channels each, so every bilinear
+// corner is ONE vectorised load per lane (16 B for float, 8 B for bf16) and a warp instruction
+// covers 32/LANES rows at once (D=32: four rows per warp, 128 contiguous bytes per corner per row).
+// The reference instead runs one scalar thread per channel (cuh:237-299) and, in backward, one
+// D-thread block per row with two barriers and a serial reduction per point (cuh:301-403).
+//
+// Per row the L*P sampling locations and attention weights are turned ONCE into compact records
+// in shared memory (cell offset + corner validity + weights) by the row's own lanes -- the
+// coordinate arithmetic of msda_coords.cuh is done once per point, not once per channel -- and
+// then broadcast-read by all lanes of the row in the gather loop.
+//
+// Backward: per point each lane forms 4 partial dot products <grad_out, corner_k> over its 4
+// channels; partials of 4 points are transposed-and-reduced across the row's lanes with a
+// butterfly of shuffles (no shared memory, no barriers), after which one lane per point finishes
+// grad_attn_weight / grad_sampling_loc and stores them.  grad_value is scattered with 128-bit
+// vector reductions (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4) -- 4x fewer atomic
+// instructions than the reference's scalar atomicAdd (cuh:125-152).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "msda_coords.cuh"
+
+namespace msda {
+
+constexpr int kFastThreads = 256;
+constexpr int kFastMaxLevels = 16;
+constexpr int kFastMaxPoints = 64;  // L*P per row
+
+// ---- 4-channel vector access --------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  float4 r;
+  r.x = __uint_as_float(u.x << 16);
+  r.y = __uint_as_float(u.x & 0xffff0000u);
+  r.z = __uint_as_float(u.y << 16);
+  r.w = __uint_as_float(u.y & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ void st4(float* p, const float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const unsigned*>(&lo);
+  u.y = *reinterpret_cast<const unsigned*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ void fma4(float4& acc, const float s, const float4 v) {
+  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+// ---- level table in shared memory ----------------------------------------------------------
+struct LevelTab {
+  int H[kFastMaxLevels];
+  int W[kFastMaxLevels];
+  int start[kFastMaxLevels];
+};
+
+__device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes, const int64_t* lsi, int L) {
+  if (threadIdx.x < L) {
+    tab->H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    tab->W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    tab->start[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+}
+
+// rows are enumerated (b, q, h) with h fastest == memory order of loc / w / out
+__device__ __forceinline__ void decode_row(int64_t row, int H, int Q, int& b, int& q, int& h) {
+  h = (int)(row % H);
+  const int64_t bq = row / H;
+  q = (int)(bq % Q);
+  b = (int)(bq / Q);
+}
+
+template <int PT>
+__device__ __forceinline__ int level_of(int pt, int P) {
+  if constexpr (PT > 0) {
+    return pt / PT;
+  } else {
+    return pt / P;
+  }
+}
+
+// =============================================================================================
+// Forward
+// =============================================================================================
+// shared memory per row: float4 cw[NP] (corner weights x attention weight, 0 for padded corners)
+//                        int    off[NP] (element offset of corner (y0,x0) of this head inside the
+//                                        image, multiple of 16; low 4 bits = corner validity)
+template <int D, typename VT, int PT>
+__global__ void __launch_bounds__(kFastThreads)
+msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                     const float* __restrict__ w, VT* __restrict__ out, int S, int H, int L, int Q, int P,
+                     int64_t rows) {
+  constexpr int LANES = D / 4;
+  constexpr int RPW = 32 / LANES;                        // rows per warp
+  constexpr int RPC = (kFastThreads / 32) * RPW;         // rows per CTA
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
+  float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
+  const int NP = L * P;
+  const int row_words = ((NP * 5 + 3) & ~3) + 4;
+
+  load_levels(tab, shapes, lsi, L);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LANES;                          // lane inside the row
+  const int rin = threadIdx.x / LANES;                   // row inside the CTA
+  const int64_t row = (int64_t)blockIdx.x * RPC + rin;
+  if (row >= rows) return;                               // whole row groups leave together (no later barrier)
+  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (lane - sub));
+
+  int b, q, h;
+  decode_row(row, H, Q, b, q, h);
+  const int HD = H * D;
+
+  float4* s_cw = reinterpret_cast<float4*>(recs + (size_t)rin * row_words);
+  int* s_off = reinterpret_cast<int*>(recs + (size_t)rin * row_words + NP * 4);
+
+  // ---- phase 1: records ----
+  {
+    const float* lp = loc + row * (int64_t)NP * 2;
+    const float* wp = w + row * (int64_t)NP;
+    for (int pt = sub; pt < NP; pt += LANES) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + pt);
+      const float aw = __ldg(wp + pt);
+      const int l = level_of<PT>(pt, P);
+      const int Hl = tab->H[l], Wl = tab->W[l];
+      const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
+      const float hh = 1.0f - c.lh, hw = 1.0f - c.lw;
+      float4 cw;
+      cw.x = (c.valid & 1u) ? hh * hw * aw : 0.0f;
+      cw.y = (c.valid & 2u) ? hh * c.lw * aw : 0.0f;
+      cw.z = (c.valid & 4u) ? c.lh * hw * aw : 0.0f;
+      cw.w = (c.valid & 8u) ? c.lh * c.lw * aw : 0.0f;
+      const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + h) * D;
+      s_cw[pt] = cw;
+      s_off[pt] = o | (int)c.valid;
+    }
+  }
+  __syncwarp(gmask);
+
+  // ---- phase 2: gather ----
+  const VT* vimg = value + (int64_t)b * S * HD + sub * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  int pt = 0;
+  for (int l = 0; l < L; ++l) {
+    const int dy = tab->W[l] * HD;
+    const int np = (PT > 0) ? PT : P;
+#pragma unroll
+    for (int p = 0; p < np; ++p, ++pt) {
+      const int oc = s_off[pt];
+      const unsigned m = (unsigned)oc & 15u;
+      if (m == 0u) continue;
+      const float4 cw = s_cw[pt];
+      const VT* p00 = vimg + (oc & ~15);
+      const float4 v00 = (m & 1u) ? ld4(p00) : zero;
+      const float4 v01 = (m & 2u) ? ld4(p00 + HD) : zero;
+      const float4 v10 = (m & 4u) ? ld4(p00 + dy) : zero;
+      const float4 v11 = (m & 8u) ? ld4(p00 + dy + HD) : zero;
+      fma4(acc, cw.x, v00);
+      fma4(acc, cw.y, v01);
+      fma4(acc, cw.z, v10);
+      fma4(acc, cw.w, v11);
+    }
+  }
+  st4(out + row * D + sub * 4, acc);
+}
+
+// =============================================================================================
+// Backward
+// =============================================================================================
+// shared memory per row: int4 rec[NP] = { off | valid, lw, lh, aw } (floats bit-cast)
+template <int LANES>
+__device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
+  // d[j*4+k]: partial dot k of point j.  After this, lane `sub` holds in d[0..3] the four dots of
+  // point sub / (LANES/4), summed over all LANES lanes of the row.
+  {
+    const bool up = (sub & (LANES / 2)) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? d[i] : d[i + 8];
+      const float keep = up ? d[i + 8] : d[i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, LANES / 2);
+    }
+  }
+  {
+    const bool up = (sub & (LANES / 4)) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? d[i] : d[i + 4];
+      const float keep = up ? d[i + 4] : d[i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, LANES / 4);
+    }
+  }
+#pragma unroll
+  for (int m = LANES / 8; m > 0; m >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], m);
+  }
+}
+
+template <int D, typename VT, int PT>
+__global__ void __launch_bounds__(kFastThreads)
+msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
+                     const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
+                     const float* __restrict__ loc, const float* __restrict__ w,
+                     float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                     float* __restrict__ grad_w, int S, int H, int L, int Q, int P, int64_t rows) {
+  constexpr int LANES = D / 4;
+  constexpr int RPW = 32 / LANES;
+  constexpr int RPC = (kFastThreads / 32) * RPW;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
+  int4* recs = reinterpret_cast<int4*>(smem_raw + sizeof(LevelTab));
+  const int NP = L * P;
+  const int row_recs = NP + 1;   // +1 record of padding spreads rows over banks
+
+  load_levels(tab, shapes, lsi, L);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LANES;
+  const int rin = threadIdx.x / LANES;
+  int64_t row = (int64_t)blockIdx.x * RPC + rin;
+  // A warp must stay converged for the full-mask shuffles below: rows past the end are clamped
+  // and simply do not write.
+  const bool live = row < rows;
+  if (!live) row = rows - 1;
+
+  int b, q, h;
+  decode_row(row, H, Q, b, q, h);
+  const int HD = H * D;
+  int4* s_rec = recs + (size_t)rin * row_recs;
+
+  {
+    const float* lp = loc + row * (int64_t)NP * 2;
+    const float* wp = w + row * (int64_t)NP;
+    for (int pt = sub; pt < NP; pt += LANES) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + pt);
+      const float aw = __ldg(wp + pt);
+      const int l = level_of<PT>(pt, P);
+      const int Hl = tab->H[l], Wl = tab->W[l];
+      const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
+      const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + h) * D;
+      int4 r;
+      r.x = o | (int)c.valid;
+      r.y = __float_as_int(c.lw);
+      r.z = __float_as_int(c.lh);
+      r.w = __float_as_int(aw);
+      s_rec[pt] = r;
+    }
+  }
+  __syncwarp();
+
+  const int64_t img = (int64_t)b * S * HD + sub * 4;
+  const VT* vimg = value + img;
+  float* gimg = grad_value + img;
+  const float4 go = ld4(grad_out + row * D + sub * 4);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* glp = grad_loc + row * (int64_t)NP * 2;
+  float* gwp = grad_w + row * (int64_t)NP;
+
+  for (int c0 = 0; c0 < NP; c0 += 4) {
+    float d[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pt = c0 + j;
+      d[4 * j + 0] = 0.f; d[4 * j + 1] = 0.f; d[4 * j + 2] = 0.f; d[4 * j + 3] = 0.f;
+      if (pt < NP) {
+        const int4 r = s_rec[pt];
+        const unsigned m = (unsigned)r.x & 15u;
+        if (m != 0u) {
+          const int l = level_of<PT>(pt, P);
+          const int dy = tab->W[l] * HD;
+          const int o = r.x & ~15;
+          const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
+          const float hh = 1.0f - lh, hw = 1.0f - lw;
+          const VT* p00 = vimg + o;
+          const float4 v00 = (m & 1u) ? ld4(p00) : zero;
+          const float4 v01 = (m & 2u) ? ld4(p00 + HD) : zero;
+          const float4 v10 = (m & 4u) ? ld4(p00 + dy) : zero;
+          const float4 v11 = (m & 8u) ? ld4(p00 + dy + HD) : zero;
+          d[4 * j + 0] = dot4(go, v00);
+          d[4 * j + 1] = dot4(go, v01);
+          d[4 * j + 2] = dot4(go, v10);
+          d[4 * j + 3] = dot4(go, v11);
+          if (live) {
+            float* g00 = gimg + o;
+            const float c00 = hh * hw * aw, c01 = hh * lw * aw, c10 = lh * hw * aw, c11 = lh * lw * aw;
+            if (m & 1u) atomicAdd(reinterpret_cast<float4*>(g00), make_float4(c00 * go.x, c00 * go.y, c00 * go.z, c00 * go.w));
+            if (m & 2u) atomicAdd(reinterpret_cast<float4*>(g00 + HD), make_float4(c01 * go.x, c01 * go.y, c01 * go.z, c01 * go.w));
+            if (m & 4u) atomicAdd(reinterpret_cast<float4*>(g00 + dy), make_float4(c10 * go.x, c10 * go.y, c10 * go.z, c10 * go.w));
+            if (m & 8u) atomicAdd(reinterpret_cast<float4*>(g00 + dy + HD), make_float4(c11 * go.x, c11 * go.y, c11 * go.z, c11 * go.w));
+          }
+        }
+      }
+    }
+    transpose_reduce_4x4<LANES>(d, sub);
+    const int mine = c0 + sub / (LANES / 4);
+    if (live && (sub % (LANES / 4)) == 0 && mine < NP) {
+      const int4 r = s_rec[mine];
+      const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
+      const float hh = 1.0f - lh, hw = 1.0f - lw;
+      const int l = level_of<PT>(mine, P);
+      // d[k] = <grad_out, v_k> with padded corners contributing 0 (cuh:119-158)
+      const float g_aw = hh * hw * d[0] + hh * lw * d[1] + lh * hw * d[2] + lh * lw * d[3];
+      const float g_x = (hh * (d[1] - d[0]) + lh * (d[3] - d[2])) * aw * (float)tab->W[l];
+      const float g_y = (hw * (d[2] - d[0]) + lw * (d[3] - d[1])) * aw * (float)tab->H[l];
+      const bool gated = ((unsigned)r.x & 15u) == 0u;   // reference leaves a gated point's grads at 0 (cuh:369)
+      gwp[mine] = gated ? 0.0f : g_aw;
+      *reinterpret_cast<float2*>(glp + 2 * mine) = gated ? make_float2(0.f, 0.f) : make_float2(g_x, g_y);
+    }
+  }
+}
+
+}  // namespace msda

@@ -1,0 +1,166 @@
+"""Operator boundary of the B200-native MSDeformAttn: the two functions the reference exposes as
+``detrex._C.ms_deform_attn_forward / ms_deform_attn_backward``
+(/root/reference/detrex/layers/csrc/vision.cpp:54-59, ms_deform_attn.h:21-62) and the autograd
+``MultiScaleDeformableAttnFunction`` built on them
+(/root/reference/detrex/layers/multi_scale_deform_attn.py:44-93), with the same names, argument
+order and error behaviour -- bound to libmsda_b200.so through ctypes instead of pybind11.
+
+Differences from the reference, all documented in SURVEY.md appendix B and DESIGN.md:
+  * bf16 ``value`` is supported (locations / weights stay float32, fp32 accumulate); the reference
+    dispatches float and double only (ms_deform_attn_cuda.cu:65);
+  * ``im2col_step`` is accepted and ignored: one launch covers the batch, so the reference's
+    ``batch % im2col_step == 0`` assert (ms_deform_attn_cuda.cu:53) has nothing to protect;
+  * a non-contiguous ``grad_output`` is made contiguous instead of asserting (cu:99);
+  * CPU tensors raise (as ms_deform_attn.h:39 does) -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes
+from typing import List
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_DTYPE_TAG = {torch.float32: _lib.MSDA_F32, torch.float64: _lib.MSDA_F64, torch.bfloat16: _lib.MSDA_BF16}
+
+_state = {"deterministic": False, "flags": 0}
+
+
+def set_deterministic(enabled: bool) -> None:
+    """Select the bit-reproducible backward (also implied by torch.use_deterministic_algorithms)."""
+    _state["deterministic"] = bool(enabled)
+
+
+@contextlib.contextmanager
+def kernel_flags(flags: int):
+    """Temporarily OR extra MSDA_FLAG_* bits into every call (tests / benchmarks)."""
+    old = _state["flags"]
+    _state["flags"] = old | int(flags)
+    try:
+        yield
+    finally:
+        _state["flags"] = old
+
+
+def _flags(backward: bool) -> int:
+    f = _state["flags"]
+    if backward and (_state["deterministic"] or torch.are_deterministic_algorithms_enabled()):
+        f |= _lib.FLAG_DETERMINISTIC
+    return f
+
+
+def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
+    # mirrors the AT_ASSERTM block of ms_deform_attn_cuda.cu:29-39
+    _require(value.is_cuda, "Not implemented on the CPU")  # ms_deform_attn.h:39
+    for name, t in (("value", value), ("spatial_shapes", spatial_shapes),
+                    ("level_start_index", level_start_index), ("sampling_loc", sampling_loc),
+                    ("attn_weight", attn_weight)):
+        _require(t.is_cuda, f"{name} must be a CUDA tensor")
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+        _require(t.device == value.device, f"{name} must be on {value.device}")
+    _require(value.dim() == 4, "value must be [B, S, H, D]")
+    _require(sampling_loc.dim() == 6 and sampling_loc.shape[-1] == 2, "sampling_loc must be [B, Q, H, L, P, 2]")
+    _require(attn_weight.dim() == 5, "attn_weight must be [B, Q, H, L, P]")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64,
+             "spatial_shapes / level_start_index must be int64")
+    B, S, H, D = value.shape
+    Bq, Q, Hq, L, P, _ = sampling_loc.shape
+    _require(Bq == B and Hq == H, "sampling_loc batch / heads do not match value")
+    _require(tuple(attn_weight.shape) == (B, Q, H, L, P), "attn_weight shape does not match sampling_loc")
+    _require(spatial_shapes.shape == (L, 2) and level_start_index.shape == (L,),
+             "spatial_shapes must be [L, 2] and level_start_index [L]")
+    _require(value.dtype in _DTYPE_TAG, f"unsupported value dtype {value.dtype} (float32, float64, bfloat16)")
+    aux = torch.float64 if value.dtype == torch.float64 else torch.float32
+    _require(sampling_loc.dtype == aux and attn_weight.dtype == aux,
+             f"sampling_loc / attn_weight must be {aux} when value is {value.dtype}")
+    return B, S, H, D, L, Q, P
+
+
+def ms_deform_attn_forward(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,
+                           sampling_loc: torch.Tensor, attn_weight: torch.Tensor, im2col_step: int = 64) -> torch.Tensor:
+    """``detrex._C.ms_deform_attn_forward`` (vision.cpp:55): returns ``[B, Q, H*D]`` in value's dtype."""
+    B, S, H, D, L, Q, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
+    stream = torch.cuda.current_stream(value.device).cuda_stream
+    status = _lib.lib().msda_forward(ctypes.c_void_p(stream), _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
+                                     _ptr(sampling_loc), _ptr(attn_weight), B, S, H, D, L, Q, P, _ptr(out),
+                                     _DTYPE_TAG[value.dtype], _flags(False))
+    _lib.check(status, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,
+                            sampling_loc: torch.Tensor, attn_weight: torch.Tensor, grad_output: torch.Tensor,
+                            im2col_step: int = 64) -> List[torch.Tensor]:
+    """``detrex._C.ms_deform_attn_backward`` (vision.cpp:56): ``[grad_value, grad_sampling_loc, grad_attn_weight]``."""
+    B, S, H, D, L, Q, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    _require(grad_output.is_cuda and grad_output.device == value.device, "grad_output must be a CUDA tensor")
+    _require(grad_output.dtype == value.dtype, "grad_output dtype must match value")
+    _require(grad_output.numel() == B * Q * H * D, "grad_output must be [B, Q, H*D]")
+    grad_output = grad_output.contiguous()
+    grad_value = torch.empty_like(value)
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_w = torch.empty_like(attn_weight)
+    flags = _flags(True)
+    tag = _DTYPE_TAG[value.dtype]
+    handle = _lib.lib()
+    ws_bytes = int(handle.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, tag, flags))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
+    stream = torch.cuda.current_stream(value.device).cuda_stream
+    status = handle.msda_backward(ctypes.c_void_p(stream), _ptr(grad_output), _ptr(value), _ptr(spatial_shapes),
+                                  _ptr(level_start_index), _ptr(sampling_loc), _ptr(attn_weight), B, S, H, D, L, Q, P,
+                                  _ptr(grad_value), _ptr(grad_loc), _ptr(grad_w),
+                                  _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, tag, flags)
+    _lib.check(status, "ms_deform_attn_backward")
+    return [grad_value, grad_loc, grad_w]
+
+
+class MultiScaleDeformableAttnFunction(Function):
+    """Same six-argument ``apply`` as the reference (multi_scale_deform_attn.py:44-54)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step):
+        ctx.im2col_step = im2col_step
+        output = ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                        attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = ctx.saved_tensors
+        grad_value, grad_sampling_loc, grad_attn_weight = ms_deform_attn_backward(
+            value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights, grad_output,
+            ctx.im2col_step)
+        return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+def debug_bookkeeping(sampling_loc: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,
+                      spatial_size: int, channels: int):
+    """Integer bookkeeping of the float kernels (test hook, see include/msda.h)."""
+    B, Q, H, L, P, _ = sampling_loc.shape
+    n = B * Q * H * L * P
+    offs = torch.empty((n, 4), dtype=torch.int64, device=sampling_loc.device)
+    frac = torch.empty((n, 2), dtype=torch.float32, device=sampling_loc.device)
+    stream = torch.cuda.current_stream(sampling_loc.device).cuda_stream
+    status = _lib.lib().msda_debug_bookkeeping(ctypes.c_void_p(stream), _ptr(sampling_loc.contiguous()),
+                                               _ptr(spatial_shapes), _ptr(level_start_index), B, spatial_size, H,
+                                               channels, L, Q, P, _ptr(offs), _ptr(frac))
+    _lib.check(status, "msda_debug_bookkeeping")
+    return offs, frac

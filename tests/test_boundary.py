@@ -1,0 +1,132 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports what
+include/msda.h declares, the Python surface has the reference's names and signatures, the
+product never touches oracle/, and the workload byte model matches SURVEY.md section 8(d)."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import ir_ads_b200
+from ir_ads_b200 import _lib, workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "msda.h")).read()
+    declared = set(re.findall(r"\b(msda_[a-z_]+)\s*\(", header))
+    assert {"msda_forward", "msda_backward", "msda_backward_workspace_bytes"} <= declared
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), f"{name} declared in include/msda.h but not exported"
+    assert _lib.lib().msda_abi_version() == _lib.ABI_VERSION
+    assert _lib.lib().msda_status_string(0) == b"MSDA_OK"
+
+
+def test_dispatch_names():
+    name = lambda D, dt, flags=0, bwd=0, L=4, P=4: _lib.lib().msda_dispatch_name(D, L, P, 22223, 8, dt, flags, bwd).decode()
+    assert name(32, _lib.MSDA_F32) == "fwd_fast_d32_f32"
+    assert name(32, _lib.MSDA_BF16, bwd=1) == "bwd_fast_d32_bf16"
+    assert name(30, _lib.MSDA_F32) == "fwd_generic_f32"
+    assert name(32, _lib.MSDA_F64) == "fwd_generic_f64"
+    assert name(32, _lib.MSDA_F32, _lib.FLAG_FORCE_GENERIC) == "fwd_generic_f32"
+    assert name(32, _lib.MSDA_F32, L=17) == "fwd_generic_f32"
+
+
+def test_argument_errors_are_returned_not_printed():
+    h = _lib.lib()
+    st = h.msda_forward(None, None, None, None, None, None, -1, 1, 1, 1, 1, 1, 1, None, 0, 0)
+    assert st == 1 and b"negative" in h.msda_last_error_message()
+    st = h.msda_forward(None, None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, None, 9, 0)
+    assert st == 1 and b"dtype" in h.msda_last_error_message()
+    with pytest.raises(_lib.MSDAError):
+        _lib.check(st, "probe")
+    # empty problem: a no-op, not a launch error
+    assert h.msda_forward(None, None, None, None, None, None, 0, 5, 8, 32, 4, 7, 4, None, 0, 0) == 0
+    assert h.msda_backward_workspace_bytes(2, 10, 8, 32, 4, 3, 4, _lib.MSDA_BF16, 0) == 2 * 10 * 8 * 32 * 4
+    assert h.msda_backward_workspace_bytes(2, 10, 8, 32, 4, 3, 4, _lib.MSDA_F32, 0) == 0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ir_ads_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "msda_oracle" not in text or f.endswith(".cuh"), f  # .cuh may cite it in comments only
+                assert "grid_sample(" not in text, f
+
+
+def test_public_surface_matches_reference():
+    from ir_ads_b200 import MultiScaleDeformableAttention, MultiScaleDeformableAttnFunction
+
+    sig = inspect.signature(MultiScaleDeformableAttention.__init__)
+    assert list(sig.parameters)[1:] == ["embed_dim", "num_heads", "num_levels", "num_points", "img2col_step",
+                                        "dropout", "batch_first"]
+    assert [p.default for p in list(sig.parameters.values())[1:]] == [256, 8, 4, 4, 64, 0.1, False]
+    fsig = inspect.signature(MultiScaleDeformableAttention.forward)
+    assert list(fsig.parameters)[1:] == ["query", "key", "value", "identity", "query_pos", "key_padding_mask",
+                                         "reference_points", "spatial_shapes", "level_start_index", "kwargs"]
+    asig = inspect.signature(MultiScaleDeformableAttnFunction.forward)
+    assert list(asig.parameters) == ["ctx", "value", "value_spatial_shapes", "value_level_start_index",
+                                     "sampling_locations", "attention_weights", "im2col_step"]
+    assert callable(ir_ads_b200.ms_deform_attn_forward) and callable(ir_ads_b200.ms_deform_attn_backward)
+
+
+def test_module_parameters_and_init():
+    from ir_ads_b200 import MultiScaleDeformableAttention
+
+    torch.manual_seed(0)
+    m = MultiScaleDeformableAttention()
+    sd = m.state_dict()
+    assert list(sd) == ["sampling_offsets.weight", "sampling_offsets.bias", "attention_weights.weight",
+                        "attention_weights.bias", "value_proj.weight", "value_proj.bias", "output_proj.weight",
+                        "output_proj.bias"]
+    assert sum(p.numel() for p in m.parameters()) == 230272
+    assert (m.im2col_step, m.embed_dim, m.num_heads, m.num_levels, m.num_points, m.batch_first) == (64, 256, 8, 4, 4, False)
+    assert torch.count_nonzero(sd["sampling_offsets.weight"]) == 0 and torch.count_nonzero(sd["attention_weights.weight"]) == 0
+    bias = sd["sampling_offsets.bias"].view(8, 4, 4, 2)
+    # head 0 points along +x, head 2 along +y, scaled by (p+1); identical on every level (py:205-217)
+    assert torch.allclose(bias[0, :, :, 0], torch.arange(1.0, 5.0).expand(4, 4)) and torch.allclose(bias[0, :, :, 1], torch.zeros(4, 4), atol=1e-6)
+    assert torch.allclose(bias[2, :, :, 1], torch.arange(1.0, 5.0).expand(4, 4))
+    assert torch.allclose(bias[1, 0, 3], torch.tensor([4.0, 4.0]), atol=1e-5)
+    bound = (6.0 / 512) ** 0.5
+    assert sd["value_proj.weight"].abs().max() <= bound and sd["value_proj.weight"].std() > 0.5 * bound / 3 ** 0.5
+    with pytest.raises(ValueError):
+        MultiScaleDeformableAttention(embed_dim=250, num_heads=8)
+
+
+def test_cpu_tensors_raise():
+    from ir_ads_b200 import MultiScaleDeformableAttnFunction
+
+    v, shapes, lsi, loc, w = workloads.make_inputs([(4, 4)], 1, 3, 2, 16, 2, "decoder", "test", 0)
+    with pytest.raises(RuntimeError, match="CPU"):
+        MultiScaleDeformableAttnFunction.apply(v, shapes, lsi, loc, w, 64)
+
+
+def test_workload_byte_model_matches_survey():
+    w2 = workloads.WORKLOADS["cfg2"]
+    assert w2.spatial_size == 22223 and w2.points == 22_756_352
+    fwd, bwd = w2.algorithmic_bytes()
+    assert round(fwd / 1e6, 1) == 637.2 and round(bwd / 1e6, 1) == 1092.3
+    w3 = workloads.WORKLOADS["cfg3"]
+    assert w3.points == 2_048_000
+    f3, b3 = w3.algorithmic_bytes()
+    assert round((f3 + b3) / 1e6, 1) == 363.2
+    w5 = workloads.WORKLOADS["cfg5"]
+    f5, b5 = w5.algorithmic_bytes()
+    assert w5.points == 55_869_440 and round((f5 + b5) / 1e6, 1) == 2905.2
+
+
+def test_workload_inputs_are_seeded_and_shaped():
+    a = workloads.make_inputs([(6, 10), (3, 5)], 2, 0, 4, 16, 4, "encoder", "model", 5)
+    b = workloads.make_inputs([(6, 10), (3, 5)], 2, 0, 4, 16, 4, "encoder", "model", 5)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    value, shapes, lsi, loc, w = a
+    assert value.shape == (2, 75, 4, 16) and loc.shape == (2, 75, 4, 2, 4, 2) and w.shape == (2, 75, 4, 2, 4)
+    assert lsi.tolist() == [0, 60] and torch.allclose(w.sum((-1, -2)), torch.ones(2, 75, 4), atol=1e-5)

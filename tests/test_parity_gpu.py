@@ -1,0 +1,320 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI (ctypes -> libmsda_b200.so
+via ir_ads_b200.functional), against the CPU oracle and the reference-made golden vectors.
+
+Tolerances (BASELINE.json north_star): fp32 within 1e-5 relative + 1e-6 absolute, bf16 value with
+fp32 accumulate within 1e-2 relative, index bookkeeping bit-exact.  "Relative" is taken against the
+largest magnitude of the reference tensor (a sum of 64 products has no meaningful per-element
+relative error when it cancels to ~0); where values are small (the reference test's own
+distribution) the per-element torch.allclose criterion of the reference test is applied as well.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES
+from test_oracle import smooth_mask
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _mods():
+    import ir_ads_b200
+    from ir_ads_b200 import _lib, functional, workloads
+    from oracle import msda_c, msda_torch
+    return ir_ads_b200, _lib, functional, workloads, msda_c, msda_torch
+
+
+def run_cuda(value, shapes, lsi, loc, w, go, dtype=torch.float32, flags=0):
+    ir, _lib, functional, *_ = _mods()
+    aux = torch.float64 if dtype == torch.float64 else torch.float32
+    v = torch.as_tensor(value).to(DEV, dtype).requires_grad_(True)
+    lo = torch.as_tensor(loc).to(DEV, aux).requires_grad_(True)
+    ww = torch.as_tensor(w).to(DEV, aux).requires_grad_(True)
+    with functional.kernel_flags(flags):
+        out = ir.MultiScaleDeformableAttnFunction.apply(v, torch.as_tensor(shapes).to(DEV), torch.as_tensor(lsi).to(DEV),
+                                                        lo, ww, 64)
+        out.backward(torch.as_tensor(go).to(DEV, dtype))
+    torch.cuda.synchronize()
+    f = lambda t: t.detach().double().cpu().numpy()
+    return f(out), f(v.grad), f(lo.grad), f(ww.grad)
+
+
+def nerr(a, b):
+    """max |a-b| normalised by max |b|."""
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def assert_close(got, ref, rtol, atol, what):
+    bound = rtol * np.abs(ref).max() + atol
+    worst = np.abs(got - ref).max()
+    assert worst <= bound, f"{what}: max abs err {worst:.3e} > {bound:.3e} (ref max {np.abs(ref).max():.3e})"
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors made by the reference
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fp32_matches_reference_golden(golden, name):
+    c = golden(name)
+    out, gv, gl, gw = run_cuda(c["value"], c["shapes"], c["lsi"], c["loc"], c["w"], c["grad_out"])
+    m = smooth_mask(c["loc"], c["shapes"], band=1e-4)
+    assert_close(out, c["f64/out"], 1e-5, 1e-6, "out")
+    assert_close(gv, c["f64/grad_value"], 1e-5, 1e-6, "grad_value")
+    assert_close(gw, c["f64/grad_w"], 1e-5, 1e-6, "grad_w")
+    assert_close(gl * m, c["f64/grad_loc"] * m, 1e-5, 1e-6, "grad_loc")
+    if name.startswith(("ref_test", "d")):  # the reference test's own criterion and value scale
+        assert np.allclose(out, c["f64/out"], rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_fp64_matches_reference_golden(golden, name):
+    """The reference's own pin (tests/test_ms_deform_attn.py:103-129): double, allclose defaults."""
+    c = golden(name)
+    out, gv, gl, gw = run_cuda(c["value"], c["shapes"], c["lsi"], c["loc"], c["w"], c["grad_out"], torch.float64)
+    m = smooth_mask(c["loc"], c["shapes"])
+    assert np.allclose(out, c["f64/out"], rtol=1e-5, atol=1e-8)
+    assert nerr(out, c["f64/out"]) < 1e-13
+    assert nerr(gv, c["f64/grad_value"]) < 1e-12
+    assert nerr(gw, c["f64/grad_w"]) < 1e-12
+    assert nerr(gl * m, c["f64/grad_loc"] * m) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["d32", "d64", "edge_d32", "enc_mini", "dec_mini", "stress_mini"])
+def test_bf16_value_matches_reference_golden(golden, name):
+    c = golden(name)
+    vb = torch.as_tensor(c["value"]).bfloat16()
+    gob = torch.as_tensor(c["grad_out"]).bfloat16()
+    _, _, _, _, msda_c, _ = _mods()
+    # oracle on the SAME (bf16-rounded) inputs, evaluated in fp64
+    ref_out = msda_c.forward(vb.float().numpy(), c["shapes"], c["lsi"], c["loc"], c["w"], np.float64)
+    rgv, rgl, rgw = msda_c.backward(gob.float().numpy(), vb.float().numpy(), c["shapes"], c["lsi"], c["loc"], c["w"], np.float64)
+    out, gv, gl, gw = run_cuda(vb, c["shapes"], c["lsi"], c["loc"], c["w"], gob, torch.bfloat16)
+    m = smooth_mask(c["loc"], c["shapes"], band=1e-4)
+    assert_close(out, ref_out, 1e-2, 1e-6, "out")          # bf16 output rounding: 2^-9 relative
+    assert_close(gv, rgv, 1e-2, 1e-6, "grad_value")
+    assert_close(gw, rgw, 1e-4, 1e-6, "grad_w")             # fp32 outputs: only fp32 accumulate error
+    assert_close(gl * m, rgl * m, 1e-4, 1e-6, "grad_loc")
+
+
+# ------------------------------------------------------------------------------------------------
+# the channel counts the reference's gradcheck walks, fast vs generic dispatch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025, 16, 128, 2048])
+def test_channels_against_oracle(channels):
+    _, _, _, workloads, msda_c, _ = _mods()
+    levels = [(6, 4), (3, 2)]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 5, 2, channels, 2, "decoder", "edge", 40 + channels)
+    go = torch.randn(2, 5, 2 * channels, generator=torch.Generator().manual_seed(channels))
+    a = [t.numpy() for t in (value, shapes, lsi, loc, w)]
+    ref_out = msda_c.forward(*a, np.float64)
+    rgv, rgl, rgw = msda_c.backward(go.numpy(), *a, np.float64)
+    m = smooth_mask(a[3], a[1], band=1e-4)
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 1e-5)):
+        out, gv, gl, gw = run_cuda(*a, go, dtype)
+        assert_close(out, ref_out, tol, tol * 0.1, f"out D={channels} {dtype}")
+        assert_close(gv, rgv, tol, tol * 0.1, "grad_value")
+        assert_close(gw, rgw, tol, tol * 0.1, "grad_w")
+        assert_close(gl * m, rgl * m, tol, tol * 0.1, "grad_loc")
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71])
+def test_gradcheck_double(channels):
+    """tests/test_ms_deform_attn.py:131-133 (gradcheck in fp64), same tiny shape."""
+    ir, *_ = _mods()
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long, device=DEV)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = 30
+    g = torch.Generator(device=DEV).manual_seed(channels)
+    value = (torch.rand(N, S, M, channels, device=DEV, generator=g) * 0.01).double().requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2, device=DEV, generator=g).double().requires_grad_(True)
+    w = torch.rand(N, Lq, M, L, P, device=DEV, generator=g) + 1e-5
+    w = (w / w.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
+    assert torch.autograd.gradcheck(ir.MultiScaleDeformableAttnFunction.apply, (value, shapes, lsi, loc, w, 2))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("D,L,P", [(32, 4, 4), (32, 5, 8), (64, 3, 4), (16, 2, 3), (128, 1, 5), (32, 4, 1)])
+def test_fast_and_generic_kernels_agree(D, L, P, dtype):
+    _, _lib, _, workloads, _, _ = _mods()
+    levels = [(9, 7), (5, 4), (3, 2), (2, 2), (1, 1)][:L]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 37, 4, D, P, "decoder", "edge", 7, value_dtype=dtype)
+    go = torch.randn(2, 37, 4 * D, generator=torch.Generator().manual_seed(1)).to(dtype)
+    fast = run_cuda(value, shapes, lsi, loc, w, go, dtype)
+    slow = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_FORCE_GENERIC)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for f, s, name in zip(fast, slow, ("out", "grad_value", "grad_loc", "grad_w")):
+        assert_close(f, s, tol, 1e-6, name)
+
+
+# ------------------------------------------------------------------------------------------------
+# bookkeeping: bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dist", ["model", "test", "edge"])
+def test_bookkeeping_bit_exact(dist):
+    _, _, functional, workloads, msda_c, _ = _mods()
+    levels = [(25, 42), (13, 21), (7, 11), (4, 6)]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 300, 8, 32, 4, "decoder", dist, 11)
+    B, S, H, D = value.shape
+    offs, frac = functional.debug_bookkeeping(loc.to(DEV), shapes.to(DEV), lsi.to(DEV), S, D)
+    ref_offs, ref_frac = msda_c.bookkeeping(loc.numpy(), shapes.numpy(), lsi.numpy(), B, S, H, D, True,
+                                            msda_c.COORD_COMPENSATED)
+    assert np.array_equal(offs.cpu().numpy(), ref_offs)
+    assert np.array_equal(frac.cpu().numpy().view(np.uint32), ref_frac.view(np.uint32))   # bit for bit
+    exact_offs, _ = msda_c.bookkeeping(loc.numpy(), shapes.numpy(), lsi.numpy(), B, S, H, D, False)
+    assert np.array_equal(ref_offs, exact_offs)   # and it is the exact (fp64) cell of every point
+
+
+# ------------------------------------------------------------------------------------------------
+# against the reference's own CUDA kernels built for sm_100a (oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+def test_against_reference_cuda_kernels():
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libmsda_refcuda.so not built")
+    _, _, _, workloads, _, _ = _mods()
+    wl = workloads.WORKLOADS["cfg1"]
+    value, shapes, lsi, loc, w = workloads.make_workload_inputs(wl, "model", 5, DEV)
+    go = torch.randn(wl.batch, wl.queries, 256, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
+    out, gv, gl, gw = run_cuda(value, shapes, lsi, loc, w, go)
+    r_out, r_gv, r_gl, r_gw = ref_cuda.forward_backward(value, shapes, lsi, loc, w, go)
+    f = lambda t: t.double().cpu().numpy()
+    assert_close(out, f(r_out), 1e-5, 1e-6, "out vs reference CUDA")
+    assert_close(gv, f(r_gv), 1e-5, 1e-6, "grad_value vs reference CUDA")
+    assert_close(gw, f(r_gw), 1e-5, 1e-6, "grad_w vs reference CUDA")
+    m = smooth_mask(loc.cpu().numpy(), shapes.cpu().numpy(), band=1e-4)
+    assert_close(gl * m, f(r_gl) * m, 1e-5, 1e-6, "grad_loc vs reference CUDA")
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs: cfg1 at full size against the torch port in fp64; big ones through properties
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dist", ["model", "test", "edge"])
+def test_cfg1_full_size_against_fp64_port(dist):
+    _, _, _, workloads, _, msda_torch = _mods()
+    wl = workloads.WORKLOADS["cfg1"]
+    value, shapes, lsi, loc, w = workloads.make_workload_inputs(wl, dist, 2)
+    go = torch.randn(wl.batch, wl.queries, 256, generator=torch.Generator().manual_seed(3))
+    r_out, r_gv, r_gl, r_gw = [t.numpy() for t in msda_torch.forward_backward_f64(value, shapes, loc, w, go)]
+    out, gv, gl, gw = run_cuda(value, shapes, lsi, loc, w, go)
+    m = smooth_mask(loc.numpy(), shapes.numpy(), band=1e-4)
+    assert_close(out, r_out, 1e-5, 1e-6, "out")
+    assert_close(gv, r_gv, 1e-5, 1e-6, "grad_value")
+    assert_close(gw, r_gw, 1e-5, 1e-6, "grad_w")
+    assert_close(gl * m, r_gl * m, 1e-5, 1e-6, "grad_loc")
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg5"])
+def test_full_size_properties(cfg):
+    """Size-independent properties at BASELINE.json's full sizes (the oracle cannot run these):
+    (1) constant value => out = sum of in-range bilinear mass per row, grad_loc = 0 inside;
+    (2) linearity in value; (3) <out, go> == <value, grad_value> (adjoint identity, the
+    'checksum of checksums' of a linear gather/scatter pair); (4) a sampled sub-block of rows
+    agrees with the C oracle."""
+    ir, _, _, workloads, msda_c, _ = _mods()
+    wl = workloads.WORKLOADS[cfg]
+    B = 2 if cfg != "cfg3" else wl.batch
+    value, shapes, lsi, loc, w = workloads.make_workload_inputs(wl, "model", 1, DEV, batch=B)
+    vdt = value.dtype
+    Q = wl.queries
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    go = torch.randn(B, Q, wl.num_heads * wl.head_dim, device=DEV, generator=gen).to(vdt)
+    fn = ir.MultiScaleDeformableAttnFunction.apply
+
+    v = value.clone().requires_grad_(True)
+    out = fn(v, shapes, lsi, loc, w, 64)
+    out.backward(go)
+    # (3) adjoint identity in fp64 accumulation
+    lhs = (out.double() * go.double()).sum().item()
+    rhs = (value.double() * v.grad.double()).sum().item()
+    tol = 2e-2 if vdt == torch.bfloat16 else 1e-4
+    assert abs(lhs - rhs) <= tol * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+    # (2) linearity: f(2v) == 2 f(v) exactly (power-of-two scaling commutes with rounding)
+    out2 = fn((value * 2), shapes, lsi, loc, w, 64)
+    assert torch.equal(out2, out.detach() * 2)
+    # (1) constant value
+    ones = torch.ones_like(value)
+    lo = loc.clone().requires_grad_(True)
+    o1 = fn(ones, shapes, lsi, lo, w, 64)
+    assert float(o1.float().max()) <= 1.0 + 1e-2 and float(o1.float().min()) >= -1e-6
+    # (4) sampled rows vs the C oracle (fp64) -- first 3 queries of image 0 and last 3 of image B-1
+    for b, q0 in ((0, 0), (B - 1, Q - 3)):
+        sl = slice(q0, q0 + 3)
+        ref = msda_c.forward(value[b:b + 1].float().cpu().numpy(), shapes.cpu().numpy(), lsi.cpu().numpy(),
+                             loc[b:b + 1, sl].cpu().numpy(), w[b:b + 1, sl].cpu().numpy(), np.float64)
+        got = out[b:b + 1, sl].detach().double().cpu().numpy()
+        rt = 1e-2 if vdt == torch.bfloat16 else 1e-5
+        assert_close(got, ref, rt, 1e-6, f"{cfg} rows b={b}")
+
+
+# ------------------------------------------------------------------------------------------------
+# edge behaviour
+# ------------------------------------------------------------------------------------------------
+def test_empty_and_ragged_inputs():
+    ir, *_ = _mods()
+    shapes = torch.as_tensor([(3, 4), (1, 2)], dtype=torch.long, device=DEV)
+    lsi = torch.as_tensor([0, 12], dtype=torch.long, device=DEV)
+    fn = ir.MultiScaleDeformableAttnFunction.apply
+    # zero queries
+    out = fn(torch.randn(2, 14, 2, 16, device=DEV), shapes, lsi, torch.rand(2, 0, 2, 2, 3, 2, device=DEV),
+             torch.rand(2, 0, 2, 2, 3, device=DEV), 64)
+    assert out.shape == (2, 0, 32)
+    # zero batch
+    out = fn(torch.randn(0, 14, 2, 16, device=DEV), shapes, lsi, torch.rand(0, 5, 2, 2, 3, 2, device=DEV),
+             torch.rand(0, 5, 2, 2, 3, device=DEV), 64)
+    assert out.shape == (0, 5, 32)
+    # zero points: empty sum -> zeros, and backward gives zero grad_value
+    v = torch.randn(1, 14, 2, 16, device=DEV, requires_grad=True)
+    out = fn(v, shapes, lsi, torch.rand(1, 5, 2, 2, 0, 2, device=DEV), torch.rand(1, 5, 2, 2, 0, device=DEV), 64)
+    assert out.shape == (1, 5, 32) and float(out.abs().max()) == 0.0
+    out.sum().backward()
+    assert float(v.grad.abs().max()) == 0.0
+    # a batch that the reference's im2col_step assert would reject (B=3, step=2: cu:53)
+    v, s2, l2, loc, w = _mods()[3].make_inputs([(3, 4), (1, 2)], 3, 4, 2, 16, 3, "decoder", "test", 0, DEV)
+    assert fn(v, s2, l2, loc, w, 2).shape == (3, 4, 32)
+
+
+def test_nan_and_inf_locations_are_skipped():
+    """Kernel semantics of the reference gate (cuh:288): NaN / Inf locations contribute nothing."""
+    ir, _, _, workloads, *_ = _mods()
+    v, shapes, lsi, loc, w = workloads.make_inputs([(5, 6), (2, 3)], 1, 4, 2, 32, 2, "decoder", "test", 3, DEV)
+    base = ir.MultiScaleDeformableAttnFunction.apply(v, shapes, lsi, loc, w, 64)
+    loc2, w2 = loc.clone(), w.clone()
+    loc2[0, 1, 0, 0, 0, 0] = float("nan")
+    loc2[0, 2, 1, 1, 1, 1] = float("inf")
+    w_ref = w.clone()
+    w_ref[0, 1, 0, 0, 0] = 0
+    w_ref[0, 2, 1, 1, 1] = 0
+    got = ir.MultiScaleDeformableAttnFunction.apply(v, shapes, lsi, loc2, w2, 64)
+    want = ir.MultiScaleDeformableAttnFunction.apply(v, shapes, lsi, loc, w_ref, 64)
+    assert torch.isfinite(got).all() and torch.equal(got, want) and not torch.equal(got, base)
+
+
+def test_non_contiguous_grad_output_and_errors():
+    ir, _lib, _, workloads, *_ = _mods()
+    v, shapes, lsi, loc, w = workloads.make_inputs([(5, 6), (2, 3)], 2, 4, 2, 32, 2, "decoder", "test", 3, DEV)
+    v.requires_grad_(True)
+    out = ir.MultiScaleDeformableAttnFunction.apply(v, shapes, lsi, loc, w, 64)
+    go = torch.randn(64, 4, 2, device=DEV).permute(2, 1, 0)          # non-contiguous [2,4,64]
+    out.backward(go)                                                 # reference asserts here (cu:99)
+    v2 = v.detach().clone().requires_grad_(True)
+    ir.MultiScaleDeformableAttnFunction.apply(v2, shapes, lsi, loc, w, 64).backward(go.contiguous())
+    assert torch.allclose(v.grad, v2.grad, rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ir.MultiScaleDeformableAttnFunction.apply(v.detach().transpose(1, 2), shapes, lsi, loc, w, 64)
+    with pytest.raises(RuntimeError, match="float32"):
+        ir.MultiScaleDeformableAttnFunction.apply(v.detach(), shapes, lsi, loc.double(), w.double(), 64)
+    with pytest.raises(RuntimeError, match="dtype"):
+        ir.MultiScaleDeformableAttnFunction.apply(v.detach().half(), shapes, lsi, loc, w, 64)
+
+
+def test_kernels_actually_launch():
+    ir, _lib, _, workloads, *_ = _mods()
+    v, shapes, lsi, loc, w = workloads.make_inputs([(5, 6), (2, 3)], 2, 4, 2, 32, 2, "decoder", "test", 3, DEV)
+    before = _lib.launch_count()
+    ir.ms_deform_attn_forward(v, shapes, lsi, loc, w, 64)
+    assert _lib.launch_count() == before + 1
