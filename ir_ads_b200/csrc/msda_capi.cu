@@ -108,46 +108,74 @@ cudaError_t ensure_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-template <int D, typename VT, int PT>
+// Persistent (TILED) kernels run one wave: SM count x resident CTAs per SM.
+template <typename K>
+cudaError_t persistent_grid(K kernel, int threads, size_t smem, unsigned* grid) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  *grid = (unsigned)(sms * per_sm);
+  return cudaSuccess;
+}
+
+// Row order: TILED needs query i == pixel i of the pyramid (encoder self-attention, Q == S).
+bool use_tiled(const Dims& d, unsigned flags) { return d.Q == d.S && !(flags & MSDA_FLAG_ORDER_LINEAR); }
+// experiment knob (bits 16-17): CTA size of the TILED kernels; 0 = default
+int tiled_threads(unsigned flags) { return ((flags >> 16) & 3u) == 1u ? 512 : 1024; }
+
+template <int D, typename VT, int PT, int THREADS, bool TILED>
 int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
                     const void* loc, const void* w, void* out) {
-  constexpr int RPC = (msda::kFastThreads / 32) * (32 / (D / 4));
+  using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
-  const size_t smem = sizeof(msda::LevelTab) + (size_t)RPC * ((((NP * 5 + 3) & ~3) + 4) * 4);
-  auto k = msda::msda_fwd_fast_kernel<D, VT, PT>;
+  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * ((((NP * 5 + 3) & ~3) + 4) * 4);
+  auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
-  const unsigned grid = (unsigned)((rows + RPC - 1) / RPC);
-  k<<<grid, msda::kFastThreads, smem, st>>>((const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
-                                            (VT*)out, d.S, d.H, d.L, d.Q, d.P, rows);
+  unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
+  if (TILED) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
+  k<<<grid, THREADS, smem, st>>>((const VT*)value, shapes, lsi, (const float*)loc, (const float*)w, (VT*)out, d.B,
+                                 d.S, d.H, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
 }
 
-template <int D, typename VT, int PT>
+template <int D, typename VT, int PT, int THREADS, bool TILED>
 int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
                     const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl, void* gw) {
-  constexpr int RPC = (msda::kFastThreads / 32) * (32 / (D / 4));
+  using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
-  const size_t smem = sizeof(msda::LevelTab) + (size_t)RPC * (NP + 1) * 16;
-  auto k = msda::msda_bwd_fast_kernel<D, VT, PT>;
+  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * (NP + 1) * 16;
+  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
-  const unsigned grid = (unsigned)((rows + RPC - 1) / RPC);
-  k<<<grid, msda::kFastThreads, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc,
-                                            (const float*)w, gv, (float*)gl, (float*)gw, d.S, d.H, d.L, d.Q, d.P,
-                                            rows);
+  unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
+  if (TILED) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
+  k<<<grid, THREADS, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
+                                 gv, (float*)gl, (float*)gw, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
 }
+
+#define MSDA_DISPATCH_ORDER(D_, VT_, PT_, CALL)                                      \
+  do {                                                                               \
+    if (!use_tiled(d, flags)) return CALL(D_, VT_, PT_, 256, false);                 \
+    if (tiled_threads(flags) == 512) return CALL(D_, VT_, PT_, 512, true);           \
+    return CALL(D_, VT_, PT_, 1024, true);                                           \
+  } while (0)
 
 #define MSDA_DISPATCH_PT(D_, VT_, CALL)                      \
   do {                                                       \
-    if (d.P == 4) { constexpr int PT_ = 4; return CALL(D_, VT_, PT_); } \
-    if (d.P == 8) { constexpr int PT_ = 8; return CALL(D_, VT_, PT_); } \
-    { constexpr int PT_ = 0; return CALL(D_, VT_, PT_); }    \
+    if (d.P == 4) MSDA_DISPATCH_ORDER(D_, VT_, 4, CALL);     \
+    if (d.P == 8) MSDA_DISPATCH_ORDER(D_, VT_, 8, CALL);     \
+    MSDA_DISPATCH_ORDER(D_, VT_, 0, CALL);                   \
   } while (0)
 
 #define MSDA_DISPATCH_D(VT_, CALL)                           \
@@ -161,17 +189,19 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
     }                                                        \
   } while (0)
 
-int fwd_fast(cudaStream_t st, const Dims& d, int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
-             const void* loc, const void* w, void* out) {
-#define CALL_FWD(D_, VT_, PT_) launch_fwd_fast<D_, VT_, PT_>(st, d, value, shapes, lsi, loc, w, out)
+int fwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* value, const int64_t* shapes,
+             const int64_t* lsi, const void* loc, const void* w, void* out) {
+#define CALL_FWD(D_, VT_, PT_, TH_, TL_) launch_fwd_fast<D_, VT_, PT_, TH_, TL_>(st, d, value, shapes, lsi, loc, w, out)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_FWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_FWD);
 #undef CALL_FWD
 }
 
-int bwd_fast(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
-             const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl, void* gw) {
-#define CALL_BWD(D_, VT_, PT_) launch_bwd_fast<D_, VT_, PT_>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw)
+int bwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* go, const void* value,
+             const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl,
+             void* gw) {
+#define CALL_BWD(D_, VT_, PT_, TH_, TL_) \
+  launch_bwd_fast<D_, VT_, PT_, TH_, TL_>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
 #undef CALL_BWD
@@ -265,7 +295,7 @@ int msda_forward(void* stream, const void* value, const int64_t* spatial_shapes,
   DeviceGuard guard;
   MSDA_CUDA(guard.enter(value));
   if (fast_ok(d, dtype, flags))
-    return fwd_fast(st, d, dtype, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
+    return fwd_fast(st, d, dtype, flags, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
   switch (dtype) {
     case MSDA_F32:
       return fwd_generic<float, float>(st, d, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output);
@@ -329,7 +359,7 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
 
   int s;
   if (fast_ok(d, dtype, flags)) {
-    s = bwd_fast(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, gv32,
+    s = bwd_fast(st, d, dtype, flags, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, gv32,
                  grad_sampling_loc, grad_attn_weight);
   } else if (dtype == MSDA_F32) {
     s = bwd_generic<float, float>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,

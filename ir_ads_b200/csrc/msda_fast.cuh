@@ -12,6 +12,16 @@
 // coordinate arithmetic of msda_coords.cuh is done once per point, not once per channel -- and
 // then broadcast-read by all lanes of the row in the gather loop.
 //
+// Row order (which rows a CTA works on; results never depend on it):
+//   LINEAR  rows in memory order (b, q, h): a CTA pass = THREADS/LANES consecutive rows.
+//   TILED   for encoder self-attention (Q == S, query i IS pixel i of the level pyramid): a
+//           persistent CTA walks work items (image, query tile, head) where a query tile is a
+//           TW x TH block of pixels of ONE level and ONE head.  Neighbouring queries sample
+//           neighbouring pixels, so the tile's gather footprint (~100 KB for 16x8 queries x 4
+//           levels, fp32) stays in the SM's L1 instead of being re-fetched from L2 per query row.
+//           The tile table is derived in-kernel from the DEVICE spatial_shapes, so no host copy of
+//           the shapes (and no sync) is needed and any grid size is correct.
+//
 // Backward: per point each lane forms 4 partial dot products <grad_out, corner_k> over its 4
 // channels; partials of 4 points are transposed-and-reduced across the row's lanes with a
 // butterfly of shuffles (no shared memory, no barriers), after which one lane per point finishes
@@ -27,7 +37,6 @@
 
 namespace msda {
 
-constexpr int kFastThreads = 256;
 constexpr int kFastMaxLevels = 16;
 constexpr int kFastMaxPoints = 64;  // L*P per row
 
@@ -57,27 +66,36 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b) {
   return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
 }
 
-// ---- level table in shared memory ----------------------------------------------------------
+// ---- level / tile table in shared memory -----------------------------------------------------
 struct LevelTab {
   int H[kFastMaxLevels];
   int W[kFastMaxLevels];
   int start[kFastMaxLevels];
+  int tiles_x[kFastMaxLevels];     // TILED only
+  int tile_begin[kFastMaxLevels];  // TILED only: first tile index of the level
+  int total_tiles;                 // TILED only
+  int pad[3];
 };
 
+template <int TW, int TH>
 __device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes, const int64_t* lsi, int L) {
   if (threadIdx.x < L) {
     tab->H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
     tab->W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
     tab->start[threadIdx.x] = (int)lsi[threadIdx.x];
   }
-}
-
-// rows are enumerated (b, q, h) with h fastest == memory order of loc / w / out
-__device__ __forceinline__ void decode_row(int64_t row, int H, int Q, int& b, int& q, int& h) {
-  h = (int)(row % H);
-  const int64_t bq = row / H;
-  q = (int)(bq % Q);
-  b = (int)(bq / Q);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < L; ++l) {
+      const int tx = (tab->W[l] + TW - 1) / TW, ty = (tab->H[l] + TH - 1) / TH;
+      tab->tiles_x[l] = tx;
+      tab->tile_begin[l] = acc;
+      acc += tx * ty;
+    }
+    tab->total_tiles = acc;
+  }
+  __syncthreads();
 }
 
 template <int PT>
@@ -89,93 +107,150 @@ __device__ __forceinline__ int level_of(int pt, int P) {
   }
 }
 
+template <int D, int THREADS>
+struct Geom {
+  static constexpr int LANES = D / 4;
+  static constexpr int RPC = THREADS / LANES;                 // rows per CTA pass
+  static constexpr int TW = (RPC >= 128) ? 16 : ((RPC >= 32) ? 8 : 4);
+  static constexpr int TH = RPC / TW;
+  static_assert(TW * TH == RPC, "tile must cover the CTA's rows");
+};
+
+struct RowRef {
+  int64_t row;   // (b*Q + q)*H + h; 0 when !live
+  int b, h;
+  bool live;
+};
+
+// Row iterator: yields this thread's row for every work item of the CTA (grid-stride).
+template <int D, int THREADS, bool TILED>
+struct RowWalk {
+  using G = Geom<D, THREADS>;
+  int64_t item, n_items, rows;
+  int rin;
+  __device__ __forceinline__ RowWalk(const LevelTab* tab, int B, int H, int64_t rows_) : rows(rows_) {
+    rin = threadIdx.x / G::LANES;
+    item = blockIdx.x;
+    n_items = TILED ? (int64_t)B * H * tab->total_tiles : (rows + G::RPC - 1) / G::RPC;
+  }
+  __device__ __forceinline__ bool done() const { return item >= n_items; }
+  __device__ __forceinline__ void next() { item += gridDim.x; }
+  __device__ __forceinline__ RowRef get(const LevelTab* tab, int L, int H, int Q) const {
+    RowRef r;
+    if (TILED) {
+      const int h = (int)(item % H);
+      const int64_t bt = item / H;
+      const int t = (int)(bt % tab->total_tiles);
+      const int b = (int)(bt / tab->total_tiles);
+      int l = 0;
+#pragma unroll 1
+      for (int k = 1; k < L; ++k)
+        if (t >= tab->tile_begin[k]) l = k;
+      const int tt = t - tab->tile_begin[l];
+      const int ty = tt / tab->tiles_x[l], tx = tt - ty * tab->tiles_x[l];
+      const int y = ty * G::TH + rin / G::TW, x = tx * G::TW + rin % G::TW;
+      const int q = tab->start[l] + y * tab->W[l] + x;
+      r.live = (y < tab->H[l]) && (x < tab->W[l]) && (q < Q);
+      r.b = b;
+      r.h = h;
+      r.row = r.live ? ((int64_t)b * Q + q) * H + h : 0;
+    } else {
+      const int64_t row = item * G::RPC + rin;
+      r.live = row < rows;
+      r.row = r.live ? row : 0;
+      r.h = (int)(r.row % H);
+      r.b = (int)(r.row / H / Q);
+    }
+    return r;
+  }
+};
+
 // =============================================================================================
 // Forward
 // =============================================================================================
 // shared memory per row: float4 cw[NP] (corner weights x attention weight, 0 for padded corners)
 //                        int    off[NP] (element offset of corner (y0,x0) of this head inside the
 //                                        image, multiple of 16; low 4 bits = corner validity)
-template <int D, typename VT, int PT>
-__global__ void __launch_bounds__(kFastThreads)
+template <int D, typename VT, int PT, int THREADS, bool TILED>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                     const float* __restrict__ w, VT* __restrict__ out, int S, int H, int L, int Q, int P,
-                     int64_t rows) {
-  constexpr int LANES = D / 4;
-  constexpr int RPW = 32 / LANES;                        // rows per warp
-  constexpr int RPC = (kFastThreads / 32) * RPW;         // rows per CTA
+                     const float* __restrict__ w, VT* __restrict__ out, int B, int S, int H, int L, int Q,
+                     int P, int64_t rows) {
+  using G = Geom<D, THREADS>;
+  constexpr int LANES = G::LANES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
   const int row_words = ((NP * 5 + 3) & ~3) + 4;
 
-  load_levels(tab, shapes, lsi, L);
-  __syncthreads();
+  load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
 
   const int lane = threadIdx.x & 31;
   const int sub = lane % LANES;                          // lane inside the row
   const int rin = threadIdx.x / LANES;                   // row inside the CTA
-  const int64_t row = (int64_t)blockIdx.x * RPC + rin;
-  if (row >= rows) return;                               // whole row groups leave together (no later barrier)
   const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (lane - sub));
-
-  int b, q, h;
-  decode_row(row, H, Q, b, q, h);
   const int HD = H * D;
-
   float4* s_cw = reinterpret_cast<float4*>(recs + (size_t)rin * row_words);
   int* s_off = reinterpret_cast<int*>(recs + (size_t)rin * row_words + NP * 4);
-
-  // ---- phase 1: records ----
-  {
-    const float* lp = loc + row * (int64_t)NP * 2;
-    const float* wp = w + row * (int64_t)NP;
-    for (int pt = sub; pt < NP; pt += LANES) {
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + pt);
-      const float aw = __ldg(wp + pt);
-      const int l = level_of<PT>(pt, P);
-      const int Hl = tab->H[l], Wl = tab->W[l];
-      const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
-      const float hh = 1.0f - c.lh, hw = 1.0f - c.lw;
-      float4 cw;
-      cw.x = (c.valid & 1u) ? hh * hw * aw : 0.0f;
-      cw.y = (c.valid & 2u) ? hh * c.lw * aw : 0.0f;
-      cw.z = (c.valid & 4u) ? c.lh * hw * aw : 0.0f;
-      cw.w = (c.valid & 8u) ? c.lh * c.lw * aw : 0.0f;
-      const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + h) * D;
-      s_cw[pt] = cw;
-      s_off[pt] = o | (int)c.valid;
-    }
-  }
-  __syncwarp(gmask);
-
-  // ---- phase 2: gather ----
-  const VT* vimg = value + (int64_t)b * S * HD + sub * 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  int pt = 0;
-  for (int l = 0; l < L; ++l) {
-    const int dy = tab->W[l] * HD;
-    const int np = (PT > 0) ? PT : P;
+
+  for (RowWalk<D, THREADS, TILED> walk(tab, B, H, rows); !walk.done(); walk.next()) {
+    const RowRef rr = walk.get(tab, L, H, Q);
+    if (rr.live) {   // whole row groups take the branch together; only group-scoped syncs inside
+      const int64_t row = rr.row;
+      // ---- phase 1: records ----
+      {
+        const float* lp = loc + row * (int64_t)NP * 2;
+        const float* wp = w + row * (int64_t)NP;
+        for (int pt = sub; pt < NP; pt += LANES) {
+          const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + pt);
+          const float aw = __ldg(wp + pt);
+          const int l = level_of<PT>(pt, P);
+          const int Hl = tab->H[l], Wl = tab->W[l];
+          const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
+          const float hh = 1.0f - c.lh, hw = 1.0f - c.lw;
+          float4 cw;
+          cw.x = (c.valid & 1u) ? hh * hw * aw : 0.0f;
+          cw.y = (c.valid & 2u) ? hh * c.lw * aw : 0.0f;
+          cw.z = (c.valid & 4u) ? c.lh * hw * aw : 0.0f;
+          cw.w = (c.valid & 8u) ? c.lh * c.lw * aw : 0.0f;
+          const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + rr.h) * D;
+          s_cw[pt] = cw;
+          s_off[pt] = o | (int)c.valid;
+        }
+      }
+      __syncwarp(gmask);
+
+      // ---- phase 2: gather ----
+      const VT* vimg = value + (int64_t)rr.b * S * HD + sub * 4;
+      float4 acc = zero;
+      int pt = 0;
+      for (int l = 0; l < L; ++l) {
+        const int dy = tab->W[l] * HD;
+        const int np = (PT > 0) ? PT : P;
 #pragma unroll
-    for (int p = 0; p < np; ++p, ++pt) {
-      const int oc = s_off[pt];
-      const unsigned m = (unsigned)oc & 15u;
-      if (m == 0u) continue;
-      const float4 cw = s_cw[pt];
-      const VT* p00 = vimg + (oc & ~15);
-      const float4 v00 = (m & 1u) ? ld4(p00) : zero;
-      const float4 v01 = (m & 2u) ? ld4(p00 + HD) : zero;
-      const float4 v10 = (m & 4u) ? ld4(p00 + dy) : zero;
-      const float4 v11 = (m & 8u) ? ld4(p00 + dy + HD) : zero;
-      fma4(acc, cw.x, v00);
-      fma4(acc, cw.y, v01);
-      fma4(acc, cw.z, v10);
-      fma4(acc, cw.w, v11);
+        for (int p = 0; p < np; ++p, ++pt) {
+          const int oc = s_off[pt];
+          const unsigned m = (unsigned)oc & 15u;
+          if (m == 0u) continue;
+          const float4 cw = s_cw[pt];
+          const VT* p00 = vimg + (oc & ~15);
+          const float4 v00 = (m & 1u) ? ld4(p00) : zero;
+          const float4 v01 = (m & 2u) ? ld4(p00 + HD) : zero;
+          const float4 v10 = (m & 4u) ? ld4(p00 + dy) : zero;
+          const float4 v11 = (m & 8u) ? ld4(p00 + dy + HD) : zero;
+          fma4(acc, cw.x, v00);
+          fma4(acc, cw.y, v01);
+          fma4(acc, cw.z, v10);
+          fma4(acc, cw.w, v11);
+        }
+      }
+      st4(out + row * D + sub * 4, acc);
+      __syncwarp(gmask);   // records are rewritten by the next work item
     }
   }
-  st4(out + row * D + sub * 4, acc);
 }
 
 // =============================================================================================
@@ -211,92 +286,87 @@ __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
   }
 }
 
-template <int D, typename VT, int PT>
-__global__ void __launch_bounds__(kFastThreads)
+template <int D, typename VT, int PT, int THREADS, bool TILED>
+__global__ void __launch_bounds__(THREADS)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ w,
                      float* __restrict__ grad_value, float* __restrict__ grad_loc,
-                     float* __restrict__ grad_w, int S, int H, int L, int Q, int P, int64_t rows) {
-  constexpr int LANES = D / 4;
-  constexpr int RPW = 32 / LANES;
-  constexpr int RPC = (kFastThreads / 32) * RPW;
+                     float* __restrict__ grad_w, int B, int S, int H, int L, int Q, int P, int64_t rows) {
+  using G = Geom<D, THREADS>;
+  constexpr int LANES = G::LANES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   int4* recs = reinterpret_cast<int4*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
   const int row_recs = NP + 1;   // +1 record of padding spreads rows over banks
 
-  load_levels(tab, shapes, lsi, L);
-  __syncthreads();
+  load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
 
   const int lane = threadIdx.x & 31;
   const int sub = lane % LANES;
   const int rin = threadIdx.x / LANES;
-  int64_t row = (int64_t)blockIdx.x * RPC + rin;
-  // A warp must stay converged for the full-mask shuffles below: rows past the end are clamped
-  // and simply do not write.
-  const bool live = row < rows;
-  if (!live) row = rows - 1;
-
-  int b, q, h;
-  decode_row(row, H, Q, b, q, h);
   const int HD = H * D;
   int4* s_rec = recs + (size_t)rin * row_recs;
-
-  {
-    const float* lp = loc + row * (int64_t)NP * 2;
-    const float* wp = w + row * (int64_t)NP;
-    for (int pt = sub; pt < NP; pt += LANES) {
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + pt);
-      const float aw = __ldg(wp + pt);
-      const int l = level_of<PT>(pt, P);
-      const int Hl = tab->H[l], Wl = tab->W[l];
-      const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
-      const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + h) * D;
-      int4 r;
-      r.x = o | (int)c.valid;
-      r.y = __float_as_int(c.lw);
-      r.z = __float_as_int(c.lh);
-      r.w = __float_as_int(aw);
-      s_rec[pt] = r;
-    }
-  }
-  __syncwarp();
-
-  const int64_t img = (int64_t)b * S * HD + sub * 4;
-  const VT* vimg = value + img;
-  float* gimg = grad_value + img;
-  const float4 go = ld4(grad_out + row * D + sub * 4);
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  float* glp = grad_loc + row * (int64_t)NP * 2;
-  float* gwp = grad_w + row * (int64_t)NP;
 
-  for (int c0 = 0; c0 < NP; c0 += 4) {
-    float d[16];
+  for (RowWalk<D, THREADS, TILED> walk(tab, B, H, rows); !walk.done(); walk.next()) {
+    // A warp stays converged for the full-mask shuffles below: rows that do not exist are mapped
+    // to row 0 with every point marked invalid, so they load nothing and never write.
+    const RowRef rr = walk.get(tab, L, H, Q);
+    const int64_t row = rr.row;
+    const bool live = rr.live;
+    {
+      const float* lp = loc + row * (int64_t)NP * 2;
+      const float* wp = w + row * (int64_t)NP;
+      for (int pt = sub; pt < NP; pt += LANES) {
+        const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + pt);
+        const float aw = __ldg(wp + pt);
+        const int l = level_of<PT>(pt, P);
+        const int Hl = tab->H[l], Wl = tab->W[l];
+        const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
+        const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + rr.h) * D;
+        int4 r;
+        r.x = o | (int)(live ? c.valid : 0u);
+        r.y = __float_as_int(c.lw);
+        r.z = __float_as_int(c.lh);
+        r.w = __float_as_int(aw);
+        s_rec[pt] = r;
+      }
+    }
+    __syncwarp();
+
+    const int64_t img = (int64_t)rr.b * S * HD + sub * 4;
+    const VT* vimg = value + img;
+    float* gimg = grad_value + img;
+    const float4 go = ld4(grad_out + row * D + sub * 4);
+    float* glp = grad_loc + row * (int64_t)NP * 2;
+    float* gwp = grad_w + row * (int64_t)NP;
+
+    for (int c0 = 0; c0 < NP; c0 += 4) {
+      float d[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int pt = c0 + j;
-      d[4 * j + 0] = 0.f; d[4 * j + 1] = 0.f; d[4 * j + 2] = 0.f; d[4 * j + 3] = 0.f;
-      if (pt < NP) {
-        const int4 r = s_rec[pt];
-        const unsigned m = (unsigned)r.x & 15u;
-        if (m != 0u) {
-          const int l = level_of<PT>(pt, P);
-          const int dy = tab->W[l] * HD;
-          const int o = r.x & ~15;
-          const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
-          const float hh = 1.0f - lh, hw = 1.0f - lw;
-          const VT* p00 = vimg + o;
-          const float4 v00 = (m & 1u) ? ld4(p00) : zero;
-          const float4 v01 = (m & 2u) ? ld4(p00 + HD) : zero;
-          const float4 v10 = (m & 4u) ? ld4(p00 + dy) : zero;
-          const float4 v11 = (m & 8u) ? ld4(p00 + dy + HD) : zero;
-          d[4 * j + 0] = dot4(go, v00);
-          d[4 * j + 1] = dot4(go, v01);
-          d[4 * j + 2] = dot4(go, v10);
-          d[4 * j + 3] = dot4(go, v11);
-          if (live) {
+      for (int j = 0; j < 4; ++j) {
+        const int pt = c0 + j;
+        d[4 * j + 0] = 0.f; d[4 * j + 1] = 0.f; d[4 * j + 2] = 0.f; d[4 * j + 3] = 0.f;
+        if (pt < NP) {
+          const int4 r = s_rec[pt];
+          const unsigned m = (unsigned)r.x & 15u;
+          if (m != 0u) {
+            const int l = level_of<PT>(pt, P);
+            const int dy = tab->W[l] * HD;
+            const int o = r.x & ~15;
+            const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
+            const float hh = 1.0f - lh, hw = 1.0f - lw;
+            const VT* p00 = vimg + o;
+            const float4 v00 = (m & 1u) ? ld4(p00) : zero;
+            const float4 v01 = (m & 2u) ? ld4(p00 + HD) : zero;
+            const float4 v10 = (m & 4u) ? ld4(p00 + dy) : zero;
+            const float4 v11 = (m & 8u) ? ld4(p00 + dy + HD) : zero;
+            d[4 * j + 0] = dot4(go, v00);
+            d[4 * j + 1] = dot4(go, v01);
+            d[4 * j + 2] = dot4(go, v10);
+            d[4 * j + 3] = dot4(go, v11);
             float* g00 = gimg + o;
             const float c00 = hh * hw * aw, c01 = hh * lw * aw, c10 = lh * hw * aw, c11 = lh * lw * aw;
             if (m & 1u) atomicAdd(reinterpret_cast<float4*>(g00), make_float4(c00 * go.x, c00 * go.y, c00 * go.z, c00 * go.w));
@@ -306,22 +376,23 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           }
         }
       }
+      transpose_reduce_4x4<LANES>(d, sub);
+      const int mine = c0 + sub / (LANES / 4);
+      if (live && (sub % (LANES / 4)) == 0 && mine < NP) {
+        const int4 r = s_rec[mine];
+        const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
+        const float hh = 1.0f - lh, hw = 1.0f - lw;
+        const int l = level_of<PT>(mine, P);
+        // d[k] = <grad_out, v_k> with padded corners contributing 0 (cuh:119-158)
+        const float g_aw = hh * hw * d[0] + hh * lw * d[1] + lh * hw * d[2] + lh * lw * d[3];
+        const float g_x = (hh * (d[1] - d[0]) + lh * (d[3] - d[2])) * aw * (float)tab->W[l];
+        const float g_y = (hw * (d[2] - d[0]) + lw * (d[3] - d[1])) * aw * (float)tab->H[l];
+        const bool gated = ((unsigned)r.x & 15u) == 0u;   // reference leaves a gated point's grads at 0 (cuh:369)
+        gwp[mine] = gated ? 0.0f : g_aw;
+        *reinterpret_cast<float2*>(glp + 2 * mine) = gated ? make_float2(0.f, 0.f) : make_float2(g_x, g_y);
+      }
     }
-    transpose_reduce_4x4<LANES>(d, sub);
-    const int mine = c0 + sub / (LANES / 4);
-    if (live && (sub % (LANES / 4)) == 0 && mine < NP) {
-      const int4 r = s_rec[mine];
-      const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
-      const float hh = 1.0f - lh, hw = 1.0f - lw;
-      const int l = level_of<PT>(mine, P);
-      // d[k] = <grad_out, v_k> with padded corners contributing 0 (cuh:119-158)
-      const float g_aw = hh * hw * d[0] + hh * lw * d[1] + lh * hw * d[2] + lh * lw * d[3];
-      const float g_x = (hh * (d[1] - d[0]) + lh * (d[3] - d[2])) * aw * (float)tab->W[l];
-      const float g_y = (hw * (d[2] - d[0]) + lw * (d[3] - d[1])) * aw * (float)tab->H[l];
-      const bool gated = ((unsigned)r.x & 15u) == 0u;   // reference leaves a gated point's grads at 0 (cuh:369)
-      gwp[mine] = gated ? 0.0f : g_aw;
-      *reinterpret_cast<float2*>(glp + 2 * mine) = gated ? make_float2(0.f, 0.f) : make_float2(g_x, g_y);
-    }
+    __syncwarp();   // records are rewritten by the next work item
   }
 }
 

@@ -31,9 +31,9 @@ def _mods():
 def run_cuda(value, shapes, lsi, loc, w, go, dtype=torch.float32, flags=0):
     ir, _lib, functional, *_ = _mods()
     aux = torch.float64 if dtype == torch.float64 else torch.float32
-    v = torch.as_tensor(value).to(DEV, dtype).requires_grad_(True)
-    lo = torch.as_tensor(loc).to(DEV, aux).requires_grad_(True)
-    ww = torch.as_tensor(w).to(DEV, aux).requires_grad_(True)
+    v = torch.as_tensor(value).detach().to(DEV, dtype).clone().requires_grad_(True)
+    lo = torch.as_tensor(loc).detach().to(DEV, aux).clone().requires_grad_(True)
+    ww = torch.as_tensor(w).detach().to(DEV, aux).clone().requires_grad_(True)
     with functional.kernel_flags(flags):
         out = ir.MultiScaleDeformableAttnFunction.apply(v, torch.as_tensor(shapes).to(DEV), torch.as_tensor(lsi).to(DEV),
                                                         lo, ww, 64)
@@ -66,7 +66,7 @@ def test_fp32_matches_reference_golden(golden, name):
     assert_close(gv, c["f64/grad_value"], 1e-5, 1e-6, "grad_value")
     assert_close(gw, c["f64/grad_w"], 1e-5, 1e-6, "grad_w")
     assert_close(gl * m, c["f64/grad_loc"] * m, 1e-5, 1e-6, "grad_loc")
-    if name.startswith(("ref_test", "d")):  # the reference test's own criterion and value scale
+    if name in ("ref_test", "d30", "d32", "d64", "d71", "d1025"):  # the reference test's own criterion and value scale
         assert np.allclose(out, c["f64/out"], rtol=1e-5, atol=1e-8)
 
 
@@ -149,6 +149,25 @@ def test_fast_and_generic_kernels_agree(D, L, P, dtype):
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     for f, s, name in zip(fast, slow, ("out", "grad_value", "grad_loc", "grad_w")):
         assert_close(f, s, tol, 1e-6, name)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("D,P,threads_knob", [(32, 4, 0), (32, 4, 1), (64, 4, 0), (16, 8, 1), (128, 2, 0), (32, 3, 0)])
+def test_tiled_and_linear_row_orders_agree(D, P, threads_knob, dtype):
+    """Encoder form (Q == S) takes the persistent TILED kernels; forcing LINEAR must give the same
+    forward bit for bit (same per-row arithmetic) and the same gradients up to atomic ordering."""
+    _, _lib, _, workloads, msda_c, _ = _mods()
+    levels = [(21, 37), (11, 19), (6, 10), (3, 5)]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 0, 4, D, P, "encoder", "model", 3, value_dtype=dtype)
+    go = torch.randn(2, value.shape[1], 4 * D, generator=torch.Generator().manual_seed(1)).to(dtype)
+    tiled = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=threads_knob << 16)
+    linear = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_ORDER_LINEAR)
+    assert np.array_equal(tiled[0], linear[0])
+    assert np.array_equal(tiled[2], linear[2]) and np.array_equal(tiled[3], linear[3])
+    assert_close(tiled[1], linear[1], 1e-5 if dtype == torch.float32 else 1e-2, 1e-6, "grad_value")
+    if dtype == torch.float32:
+        ref = msda_c.forward(value.numpy(), shapes.numpy(), lsi.numpy(), loc.numpy(), w.numpy(), np.float64)
+        assert_close(tiled[0], ref, 1e-5, 1e-6, "tiled out vs oracle")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -240,7 +259,7 @@ def test_full_size_properties(cfg):
     ones = torch.ones_like(value)
     lo = loc.clone().requires_grad_(True)
     o1 = fn(ones, shapes, lsi, lo, w, 64)
-    assert float(o1.float().max()) <= 1.0 + 1e-2 and float(o1.float().min()) >= -1e-6
+    assert float(o1.detach().float().max()) <= 1.0 + 1e-2 and float(o1.detach().float().min()) >= -1e-6
     # (4) sampled rows vs the C oracle (fp64) -- first 3 queries of image 0 and last 3 of image B-1
     for b, q0 in ((0, 0), (B - 1, Q - 3)):
         sl = slice(q0, q0 + 3)
