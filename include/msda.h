@@ -66,9 +66,18 @@ extern "C" {
 #define MSDA_ERR_CUDA 4             /* a CUDA runtime call or kernel launch failed; see msda_last_error_message */
 
 /* flags (bit set) */
-#define MSDA_FLAG_DETERMINISTIC (1u << 0) /* backward: bit-reproducible grad_value (no float atomics) */
+/* Backward: bit-reproducible grad_value.  Contributions are accumulated as 64-bit fixed point
+ * (integer atomics commute, float atomics do not) with a power-of-two scale derived from
+ * max|grad_output| * max|attn_weight|, then converted once: run-to-run identical, absolute error
+ * <= 2^-38 of that bound per contribution, headroom for 2^25 maximal contributions per element.
+ * grad_sampling_loc / grad_attn_weight are reproducible in every mode (fixed reduction order). */
+#define MSDA_FLAG_DETERMINISTIC (1u << 0)
 #define MSDA_FLAG_FORCE_GENERIC (1u << 1) /* bypass the D in {16,32,64,128} fast kernels             */
-#define MSDA_FLAG_ORDER_LINEAR (1u << 2)  /* rows processed in memory order (no locality re-ordering) */
+#define MSDA_FLAG_ORDER_LINEAR (1u << 2)  /* rows processed in memory order (the default)              */
+/* Encoder form only (Q == S): persistent CTAs walk (image, pyramid tile, head) work items so that a
+ * tile's gather footprint stays in L1.  Same results; measured slower than LINEAR so far,
+ * hence opt-in.  Bits 16-17 are an unstable tuning knob of these kernels (CTA size). */
+#define MSDA_FLAG_ORDER_TILED (1u << 3)
 
 int msda_abi_version(void);
 

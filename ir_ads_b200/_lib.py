@@ -20,6 +20,7 @@ MSDA_OK = 0
 FLAG_DETERMINISTIC = 1 << 0
 FLAG_FORCE_GENERIC = 1 << 1
 FLAG_ORDER_LINEAR = 1 << 2
+FLAG_ORDER_TILED = 1 << 3
 ABI_VERSION = 1
 
 _lock = threading.Lock()

@@ -124,7 +124,9 @@ cudaError_t persistent_grid(K kernel, int threads, size_t smem, unsigned* grid) 
 }
 
 // Row order: TILED needs query i == pixel i of the pyramid (encoder self-attention, Q == S).
-bool use_tiled(const Dims& d, unsigned flags) { return d.Q == d.S && !(flags & MSDA_FLAG_ORDER_LINEAR); }
+bool use_tiled(const Dims& d, unsigned flags) {
+  return d.Q == d.S && (flags & MSDA_FLAG_ORDER_TILED) && !(flags & MSDA_FLAG_ORDER_LINEAR);
+}
 // experiment knob (bits 16-17): CTA size of the TILED kernels; 0 = default
 int tiled_threads(unsigned flags) { return ((flags >> 16) & 3u) == 1u ? 512 : 1024; }
 
@@ -133,7 +135,7 @@ int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int
                     const void* loc, const void* w, void* out) {
   using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
-  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * ((((NP * 5 + 3) & ~3) + 4) * 4);
+  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::fwd_row_words(NP) * 4;
   auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
@@ -146,19 +148,20 @@ int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int
   return MSDA_OK;
 }
 
-template <int D, typename VT, int PT, int THREADS, bool TILED>
+template <int D, typename VT, int PT, int THREADS, bool TILED, typename ACC>
 int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
-                    const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl, void* gw) {
+                    const int64_t* lsi, const void* loc, const void* w, ACC* gv, void* gl, void* gw,
+                    const msda::DetScale* det) {
   using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
-  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * (NP + 1) * 16;
-  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED>;
+  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::bwd_row_words(NP) * 4;
+  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
   if (TILED) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
   k<<<grid, THREADS, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
-                                 gv, (float*)gl, (float*)gw, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
+                                 gv, (float*)gl, (float*)gw, det, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
@@ -201,7 +204,20 @@ int bwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const vo
              const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl,
              void* gw) {
 #define CALL_BWD(D_, VT_, PT_, TH_, TL_) \
-  launch_bwd_fast<D_, VT_, PT_, TH_, TL_>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw)
+  launch_bwd_fast<D_, VT_, PT_, TH_, TL_, float>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw, nullptr)
+  if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
+  MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
+#undef CALL_BWD
+}
+
+// deterministic accumulate: LINEAR order only
+int bwd_fast_det(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
+                 const int64_t* lsi, const void* loc, const void* w, unsigned long long* acc, void* gl, void* gw,
+                 const msda::DetScale* det) {
+  const unsigned flags = MSDA_FLAG_ORDER_LINEAR;
+#define CALL_BWD(D_, VT_, PT_, TH_, TL_)                                                                      \
+  launch_bwd_fast<D_, VT_, PT_, 256, false, unsigned long long>(st, d, go, value, shapes, lsi, loc, w, acc, gl, \
+                                                                gw, det)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
 #undef CALL_BWD
@@ -223,16 +239,17 @@ int fwd_generic(cudaStream_t st, const Dims& d, const void* value, const int64_t
   return MSDA_OK;
 }
 
-template <typename VT, typename CT>
+template <typename VT, typename CT, typename ACC>
 int bwd_generic(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
-                const int64_t* lsi, const void* loc, const void* w, CT* gv, void* gl, void* gw) {
+                const int64_t* lsi, const void* loc, const void* w, ACC* gv, void* gl, void* gw,
+                const msda::DetScale* det = nullptr) {
   int threads = 32;
   while (threads < d.D && threads < 256) threads <<= 1;
   const int64_t rows = d.rows();
   const int grid = (int)(rows < 148 * 64 ? rows : 148 * 64);
-  msda::msda_bwd_generic_kernel<VT, CT><<<grid, threads, 0, st>>>((const VT*)go, (const VT*)value, shapes, lsi,
-                                                                  (const CT*)loc, (const CT*)w, gv, (CT*)gl, (CT*)gw,
-                                                                  d.S, d.H, d.D, d.L, d.Q, d.P, rows);
+  msda::msda_bwd_generic_kernel<VT, CT, ACC><<<grid, threads, 0, st>>>(
+      (const VT*)go, (const VT*)value, shapes, lsi, (const CT*)loc, (const CT*)w, gv, (CT*)gl, (CT*)gw, det, d.S, d.H,
+      d.D, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
@@ -308,10 +325,13 @@ int msda_forward(void* stream, const void* value, const int64_t* spatial_shapes,
 
 size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels, int num_levels,
                                      int num_query, int num_point, int dtype, unsigned flags) {
-  (void)num_levels; (void)num_query; (void)num_point; (void)flags;
+  (void)num_levels; (void)num_query; (void)num_point;
   if (batch <= 0 || spatial_size <= 0 || num_heads <= 0 || channels <= 0) return 0;
+  const size_t n_value = (size_t)batch * spatial_size * num_heads * channels;
+  // deterministic: 64-bit fixed-point accumulators + {amax bits x2, DetScale}
+  if (flags & MSDA_FLAG_DETERMINISTIC) return n_value * sizeof(long long) + 64;
   // bf16 grad_value is accumulated in float and converted at the end
-  if (dtype == MSDA_BF16) return (size_t)batch * spatial_size * num_heads * channels * sizeof(float);
+  if (dtype == MSDA_BF16) return n_value * sizeof(float);
   return 0;
 }
 
@@ -331,7 +351,9 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
   if (!anchor) return fail(MSDA_ERR_INVALID_ARGUMENT, "gradient output pointer is null");
   DeviceGuard guard;
   MSDA_CUDA(guard.enter(anchor));
-  if (d.n_value()) {
+  const bool det = (flags & MSDA_FLAG_DETERMINISTIC) != 0;
+  const bool have_samples = d.n_points() != 0 && d.n_value() != 0;
+  if (d.n_value() && !(det && have_samples)) {   // the deterministic path writes grad_value in its finalize pass
     if (!grad_value) return fail(MSDA_ERR_INVALID_ARGUMENT, "grad_value is null");
     MSDA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)d.n_value() * es, st));
   }
@@ -342,42 +364,86 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
     MSDA_CUDA(cudaMemsetAsync(grad_attn_weight, 0, (size_t)d.n_points() * ls, st));
     return MSDA_OK;
   }
-  if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight)
+  if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_value)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
-  if (flags & MSDA_FLAG_DETERMINISTIC)
-    return fail(MSDA_ERR_UNSUPPORTED, "deterministic backward is not implemented in this build");
+  const size_t need = msda_backward_workspace_bytes(batch, spatial_size, num_heads, channels, num_levels, num_query,
+                                                    num_point, dtype, flags);
+  if (need && (!workspace || workspace_bytes < need))
+    return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, workspace_bytes);
+  auto count = [] { g_launches.fetch_add(1, std::memory_order_relaxed); };
+
+  if (det) {
+    // ---- bit-reproducible grad_value: 64-bit fixed-point accumulation (see include/msda.h) ----
+    const int64_t nv = d.n_value(), n_out = d.rows() * d.D, n_pts = d.n_points();
+    auto* acc = static_cast<unsigned long long*>(workspace);
+    auto* amax = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + (size_t)nv * 8);
+    auto* scale = reinterpret_cast<msda::DetScale*>(static_cast<char*>(workspace) + (size_t)nv * 8 + 16);
+    MSDA_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    const int g_out = grid_for(n_out, 256, 148 * 8), g_pts = grid_for(n_pts, 256, 148 * 8);
+    if (dtype == MSDA_F32) msda::msda_amax_kernel<float><<<g_out, 256, 0, st>>>((const float*)grad_output, n_out, amax);
+    else if (dtype == MSDA_F64) msda::msda_amax_kernel<double><<<g_out, 256, 0, st>>>((const double*)grad_output, n_out, amax);
+    else msda::msda_amax_kernel<__nv_bfloat16><<<g_out, 256, 0, st>>>((const __nv_bfloat16*)grad_output, n_out, amax);
+    count();
+    if (dtype == MSDA_F64) msda::msda_amax_kernel<double><<<g_pts, 256, 0, st>>>((const double*)attn_weight, n_pts, amax + 1);
+    else msda::msda_amax_kernel<float><<<g_pts, 256, 0, st>>>((const float*)attn_weight, n_pts, amax + 1);
+    count();
+    msda::msda_det_scale_kernel<<<1, 1, 0, st>>>(amax, scale, dtype == MSDA_F64 ? 44 : 38);
+    count();
+    MSDA_CUDA(cudaGetLastError());
+    int s;
+    if (fast_ok(d, dtype, flags))
+      s = bwd_fast_det(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                       acc, grad_sampling_loc, grad_attn_weight, scale);
+    else if (dtype == MSDA_F32)
+      s = bwd_generic<float, float, unsigned long long>(st, d, grad_output, value, spatial_shapes, level_start_index,
+                                                        sampling_loc, attn_weight, acc, grad_sampling_loc,
+                                                        grad_attn_weight, scale);
+    else if (dtype == MSDA_F64)
+      s = bwd_generic<double, double, unsigned long long>(st, d, grad_output, value, spatial_shapes, level_start_index,
+                                                          sampling_loc, attn_weight, acc, grad_sampling_loc,
+                                                          grad_attn_weight, scale);
+    else
+      s = bwd_generic<__nv_bfloat16, float, unsigned long long>(st, d, grad_output, value, spatial_shapes,
+                                                                level_start_index, sampling_loc, attn_weight, acc,
+                                                                grad_sampling_loc, grad_attn_weight, scale);
+    if (s != MSDA_OK) return s;
+    const int g_val = grid_for(nv, 256, 148 * 16);
+    const long long* cacc = reinterpret_cast<const long long*>(acc);
+    if (dtype == MSDA_F32) msda::msda_det_finalize_kernel<float><<<g_val, 256, 0, st>>>(cacc, (float*)grad_value, nv, scale);
+    else if (dtype == MSDA_F64) msda::msda_det_finalize_kernel<double><<<g_val, 256, 0, st>>>(cacc, (double*)grad_value, nv, scale);
+    else msda::msda_det_finalize_kernel<__nv_bfloat16><<<g_val, 256, 0, st>>>(cacc, (__nv_bfloat16*)grad_value, nv, scale);
+    count();
+    MSDA_CUDA(cudaGetLastError());
+    return MSDA_OK;
+  }
 
   float* gv32 = static_cast<float*>(grad_value);
   if (dtype == MSDA_BF16) {
-    const size_t need = msda_backward_workspace_bytes(batch, spatial_size, num_heads, channels, num_levels, num_query,
-                                                      num_point, dtype, flags);
-    if (!workspace || workspace_bytes < need)
-      return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, workspace_bytes);
     gv32 = static_cast<float*>(workspace);
     MSDA_CUDA(cudaMemsetAsync(gv32, 0, need, st));
   }
 
   int s;
   if (fast_ok(d, dtype, flags)) {
-    s = bwd_fast(st, d, dtype, flags, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, gv32,
-                 grad_sampling_loc, grad_attn_weight);
+    s = bwd_fast(st, d, dtype, flags, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                 gv32, grad_sampling_loc, grad_attn_weight);
   } else if (dtype == MSDA_F32) {
-    s = bwd_generic<float, float>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
-                                  attn_weight, gv32, grad_sampling_loc, grad_attn_weight);
+    s = bwd_generic<float, float, float>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                                         attn_weight, gv32, grad_sampling_loc, grad_attn_weight);
   } else if (dtype == MSDA_F64) {
-    s = bwd_generic<double, double>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
-                                    attn_weight, static_cast<double*>(grad_value), grad_sampling_loc,
-                                    grad_attn_weight);
+    s = bwd_generic<double, double, double>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                                            attn_weight, static_cast<double*>(grad_value), grad_sampling_loc,
+                                            grad_attn_weight);
   } else {
-    s = bwd_generic<__nv_bfloat16, float>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
-                                          attn_weight, gv32, grad_sampling_loc, grad_attn_weight);
+    s = bwd_generic<__nv_bfloat16, float, float>(st, d, grad_output, value, spatial_shapes, level_start_index,
+                                                 sampling_loc, attn_weight, gv32, grad_sampling_loc, grad_attn_weight);
   }
   if (s != MSDA_OK) return s;
   if (dtype == MSDA_BF16) {
     const int64_t n = d.n_value();
     msda::msda_cast_f32_to_bf16_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
         gv32, static_cast<__nv_bfloat16*>(grad_value), n);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count();
     MSDA_CUDA(cudaGetLastError());
   }
   return MSDA_OK;

@@ -17,6 +17,13 @@
 
 namespace msda {
 
+// Fixed-point scale of the deterministic backward (MSDA_FLAG_DETERMINISTIC): written on the device
+// by msda_det_scale_kernel into the caller's workspace, read by the backward kernels.
+struct DetScale {
+  float scale;      // 2^k
+  float inv_scale;  // 2^-k (NaN when the inputs were not finite)
+};
+
 template <typename T>
 struct AxisSplit {
   int low;     // floor(coord) (0 when !ok)

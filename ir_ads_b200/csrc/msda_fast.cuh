@@ -122,6 +122,40 @@ struct RowRef {
   bool live;
 };
 
+// ---- asynchronous staging of a row's raw locations / weights (global -> shared, no registers) ----
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// shared-memory words per row (host and device must agree)
+__host__ __device__ constexpr int fwd_row_words(int NP) {
+  // float4 cw[NP] | int off[NP] | float2 raw_xy[NP] (8-byte aligned) | float raw_w[NP] | pad
+  return ((((5 * NP + 1) & ~1) + 3 * NP + 3) & ~3) + 4;
+}
+__host__ __device__ constexpr int bwd_row_words(int NP) {
+  // int4 rec[NP] | float2 raw_xy[NP] | float raw_w[NP] | pad
+  return ((7 * NP + 3) & ~3) + 4;
+}
+
+template <int LANES>
+__device__ __forceinline__ void stage_row(float2* raw_xy, float* raw_w, const float* loc, const float* w,
+                                          const RowRef& rr, int NP, int sub) {
+  if (rr.live) {
+    const float2* lp = reinterpret_cast<const float2*>(loc + rr.row * (int64_t)NP * 2);
+    const float* wp = w + rr.row * (int64_t)NP;
+    for (int pt = sub; pt < NP; pt += LANES) {
+      cp_async8(raw_xy + pt, lp + pt);
+      cp_async4(raw_w + pt, wp + pt);
+    }
+  }
+}
+
 // Row iterator: yields this thread's row for every work item of the CTA (grid-stride).
 template <int D, int THREADS, bool TILED>
 struct RowWalk {
@@ -134,7 +168,8 @@ struct RowWalk {
     n_items = TILED ? (int64_t)B * H * tab->total_tiles : (rows + G::RPC - 1) / G::RPC;
   }
   __device__ __forceinline__ bool done() const { return item >= n_items; }
-  __device__ __forceinline__ void next() { item += gridDim.x; }
+  // LINEAR kernels are launched with one CTA per item: a single pass, no loop-carried state.
+  __device__ __forceinline__ void next() { item = TILED ? item + gridDim.x : n_items; }
   __device__ __forceinline__ RowRef get(const LevelTab* tab, int L, int H, int Q) const {
     RowRef r;
     if (TILED) {
@@ -168,11 +203,14 @@ struct RowWalk {
 // =============================================================================================
 // Forward
 // =============================================================================================
-// shared memory per row: float4 cw[NP] (corner weights x attention weight, 0 for padded corners)
-//                        int    off[NP] (element offset of corner (y0,x0) of this head inside the
-//                                        image, multiple of 16; low 4 bits = corner validity)
+// Software pipeline per warp (persistent TILED CTAs; LINEAR runs it once):
+//   wait for this item's raw loc/w in shared memory  ->  phase 1: records  ->  issue cp.async for
+//   the NEXT item's loc/w  ->  phase 2: gather (the long phase, hides the HBM latency of the copy).
+// records per row: float4 cw[NP] (corner weights x attention weight, 0 for padded corners),
+//                  int off[NP]   (element offset of corner (y0,x0) of this head inside the image,
+//                                 multiple of 16; low 4 bits = corner validity)
 template <int D, typename VT, int PT, int THREADS, bool TILED>
-__global__ void __launch_bounds__(THREADS, 2048 / THREADS)
+__global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 3 : 1)
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ w, VT* __restrict__ out, int B, int S, int H, int L, int Q,
@@ -183,48 +221,56 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
-  const int row_words = ((NP * 5 + 3) & ~3) + 4;
+  const int row_words = fwd_row_words(NP);
 
   load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
 
-  const int lane = threadIdx.x & 31;
-  const int sub = lane % LANES;                          // lane inside the row
+  const int sub = (threadIdx.x & 31) % LANES;            // lane inside the row
   const int rin = threadIdx.x / LANES;                   // row inside the CTA
-  const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (lane - sub));
   const int HD = H * D;
-  float4* s_cw = reinterpret_cast<float4*>(recs + (size_t)rin * row_words);
-  int* s_off = reinterpret_cast<int*>(recs + (size_t)rin * row_words + NP * 4);
+  float* my = recs + (size_t)rin * row_words;
+  float4* s_cw = reinterpret_cast<float4*>(my);
+  int* s_off = reinterpret_cast<int*>(my + 4 * NP);
+  float2* raw_xy = reinterpret_cast<float2*>(my + ((5 * NP + 1) & ~1));
+  float* raw_w = my + ((5 * NP + 1) & ~1) + 2 * NP;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (RowWalk<D, THREADS, TILED> walk(tab, B, H, rows); !walk.done(); walk.next()) {
-    const RowRef rr = walk.get(tab, L, H, Q);
-    if (rr.live) {   // whole row groups take the branch together; only group-scoped syncs inside
-      const int64_t row = rr.row;
-      // ---- phase 1: records ----
-      {
-        const float* lp = loc + row * (int64_t)NP * 2;
-        const float* wp = w + row * (int64_t)NP;
-        for (int pt = sub; pt < NP; pt += LANES) {
-          const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + pt);
-          const float aw = __ldg(wp + pt);
-          const int l = level_of<PT>(pt, P);
-          const int Hl = tab->H[l], Wl = tab->W[l];
-          const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
-          const float hh = 1.0f - c.lh, hw = 1.0f - c.lw;
-          float4 cw;
-          cw.x = (c.valid & 1u) ? hh * hw * aw : 0.0f;
-          cw.y = (c.valid & 2u) ? hh * c.lw * aw : 0.0f;
-          cw.z = (c.valid & 4u) ? c.lh * hw * aw : 0.0f;
-          cw.w = (c.valid & 8u) ? c.lh * c.lw * aw : 0.0f;
-          const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + rr.h) * D;
-          s_cw[pt] = cw;
-          s_off[pt] = o | (int)c.valid;
-        }
+  RowWalk<D, THREADS, TILED> walk(tab, B, H, rows);
+  if (walk.done()) return;
+  RowRef cur = walk.get(tab, L, H, Q);
+  stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
+  while (true) {
+    walk.next();
+    const bool has_next = !walk.done();
+    RowRef nxt = cur;
+    if (has_next) nxt = walk.get(tab, L, H, Q);
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- phase 1: records ----
+    if (cur.live) {
+      for (int pt = sub; pt < NP; pt += LANES) {
+        const float2 xy = raw_xy[pt];
+        const float aw = raw_w[pt];
+        const int l = level_of<PT>(pt, P);
+        const int Hl = tab->H[l], Wl = tab->W[l];
+        const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
+        const float hh = 1.0f - c.lh, hw = 1.0f - c.lw;
+        float4 cw;
+        cw.x = (c.valid & 1u) ? hh * hw * aw : 0.0f;
+        cw.y = (c.valid & 2u) ? hh * c.lw * aw : 0.0f;
+        cw.z = (c.valid & 4u) ? c.lh * hw * aw : 0.0f;
+        cw.w = (c.valid & 8u) ? c.lh * c.lw * aw : 0.0f;
+        const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + cur.h) * D;
+        s_cw[pt] = cw;
+        s_off[pt] = o | (int)c.valid;
       }
-      __syncwarp(gmask);
+    }
+    __syncwarp();
+    if (has_next) stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
 
-      // ---- phase 2: gather ----
-      const VT* vimg = value + (int64_t)rr.b * S * HD + sub * 4;
+    // ---- phase 2: gather ----
+    if (cur.live) {
+      const VT* vimg = value + (int64_t)cur.b * S * HD + sub * 4;
       float4 acc = zero;
       int pt = 0;
       for (int l = 0; l < L; ++l) {
@@ -247,16 +293,32 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
           fma4(acc, cw.w, v11);
         }
       }
-      st4(out + row * D + sub * 4, acc);
-      __syncwarp(gmask);   // records are rewritten by the next work item
+      st4(out + cur.row * D + sub * 4, acc);
     }
+    if (!has_next) break;
+    __syncwarp();   // records are rewritten by the next work item
+    cur = nxt;
   }
 }
 
 // =============================================================================================
 // Backward
 // =============================================================================================
-// shared memory per row: int4 rec[NP] = { off | valid, lw, lh, aw } (floats bit-cast)
+// records per row: int4 rec[NP] = { off | valid, lw, lh, aw } (floats bit-cast)
+//
+// grad_value accumulation: float (vector red, fast, order-dependent rounding) or, for
+// MSDA_FLAG_DETERMINISTIC, 64-bit fixed point (integer red: the sum is order independent).
+__device__ __forceinline__ void scatter4(float* g, const float c, const float4 go, float /*scale*/) {
+  atomicAdd(reinterpret_cast<float4*>(g), make_float4(c * go.x, c * go.y, c * go.z, c * go.w));
+}
+__device__ __forceinline__ void scatter4(unsigned long long* g, const float c, const float4 go, float scale) {
+  // c*go is rounded to float exactly as in the float path, then scaled by a power of two (exact)
+  atomicAdd(g + 0, (unsigned long long)__float2ll_rn((c * go.x) * scale));
+  atomicAdd(g + 1, (unsigned long long)__float2ll_rn((c * go.y) * scale));
+  atomicAdd(g + 2, (unsigned long long)__float2ll_rn((c * go.z) * scale));
+  atomicAdd(g + 3, (unsigned long long)__float2ll_rn((c * go.w) * scale));
+}
+
 template <int LANES>
 __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
   // d[j*4+k]: partial dot k of point j.  After this, lane `sub` holds in d[0..3] the four dots of
@@ -286,62 +348,77 @@ __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
   }
 }
 
-template <int D, typename VT, int PT, int THREADS, bool TILED>
+template <int D, typename VT, int PT, int THREADS, bool TILED, typename ACC>
 __global__ void __launch_bounds__(THREADS)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ w,
-                     float* __restrict__ grad_value, float* __restrict__ grad_loc,
-                     float* __restrict__ grad_w, int B, int S, int H, int L, int Q, int P, int64_t rows) {
+                     ACC* __restrict__ grad_value, float* __restrict__ grad_loc,
+                     float* __restrict__ grad_w, const DetScale* __restrict__ det, int B, int S, int H, int L,
+                     int Q, int P, int64_t rows) {
   using G = Geom<D, THREADS>;
   constexpr int LANES = G::LANES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
-  int4* recs = reinterpret_cast<int4*>(smem_raw + sizeof(LevelTab));
+  float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
-  const int row_recs = NP + 1;   // +1 record of padding spreads rows over banks
+  const int row_words = bwd_row_words(NP);
 
   load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
 
-  const int lane = threadIdx.x & 31;
-  const int sub = lane % LANES;
+  const int sub = (threadIdx.x & 31) % LANES;
   const int rin = threadIdx.x / LANES;
   const int HD = H * D;
-  int4* s_rec = recs + (size_t)rin * row_recs;
+  float* my = recs + (size_t)rin * row_words;
+  int4* s_rec = reinterpret_cast<int4*>(my);
+  float2* raw_xy = reinterpret_cast<float2*>(my + 4 * NP);
+  float* raw_w = my + 6 * NP;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float gscale = det ? det->scale : 1.0f;
 
-  for (RowWalk<D, THREADS, TILED> walk(tab, B, H, rows); !walk.done(); walk.next()) {
-    // A warp stays converged for the full-mask shuffles below: rows that do not exist are mapped
-    // to row 0 with every point marked invalid, so they load nothing and never write.
-    const RowRef rr = walk.get(tab, L, H, Q);
-    const int64_t row = rr.row;
-    const bool live = rr.live;
-    {
-      const float* lp = loc + row * (int64_t)NP * 2;
-      const float* wp = w + row * (int64_t)NP;
-      for (int pt = sub; pt < NP; pt += LANES) {
-        const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + pt);
-        const float aw = __ldg(wp + pt);
+  // A warp stays converged for the full-mask shuffles below: rows that do not exist (edge tiles,
+  // the tail of the last CTA) have every point marked invalid, so they load nothing, scatter
+  // nothing and never write.
+  RowWalk<D, THREADS, TILED> walk(tab, B, H, rows);
+  if (walk.done()) return;
+  RowRef cur = walk.get(tab, L, H, Q);
+  stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
+  float4 go = cur.live ? ld4(grad_out + cur.row * D + sub * 4) : zero;
+  while (true) {
+    walk.next();
+    const bool has_next = !walk.done();
+    RowRef nxt = cur;
+    if (has_next) nxt = walk.get(tab, L, H, Q);
+    cp_async_wait_all();
+    __syncwarp();
+    for (int pt = sub; pt < NP; pt += LANES) {
+      int4 r = make_int4(0, 0, 0, 0);
+      if (cur.live) {
+        const float2 xy = raw_xy[pt];
+        const float aw = raw_w[pt];
         const int l = level_of<PT>(pt, P);
         const int Hl = tab->H[l], Wl = tab->W[l];
         const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
-        const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + rr.h) * D;
-        int4 r;
-        r.x = o | (int)(live ? c.valid : 0u);
+        const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + cur.h) * D;
+        r.x = o | (int)c.valid;
         r.y = __float_as_int(c.lw);
         r.z = __float_as_int(c.lh);
         r.w = __float_as_int(aw);
-        s_rec[pt] = r;
       }
+      s_rec[pt] = r;
     }
     __syncwarp();
+    float4 go_next = zero;
+    if (has_next) {
+      stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
+      if (nxt.live) go_next = ld4(grad_out + nxt.row * D + sub * 4);
+    }
 
-    const int64_t img = (int64_t)rr.b * S * HD + sub * 4;
+    const int64_t img = (int64_t)cur.b * S * HD + sub * 4;
     const VT* vimg = value + img;
-    float* gimg = grad_value + img;
-    const float4 go = ld4(grad_out + row * D + sub * 4);
-    float* glp = grad_loc + row * (int64_t)NP * 2;
-    float* gwp = grad_w + row * (int64_t)NP;
+    ACC* gimg = grad_value + img;
+    float* glp = grad_loc + cur.row * (int64_t)NP * 2;
+    float* gwp = grad_w + cur.row * (int64_t)NP;
 
     for (int c0 = 0; c0 < NP; c0 += 4) {
       float d[16];
@@ -367,18 +444,18 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             d[4 * j + 1] = dot4(go, v01);
             d[4 * j + 2] = dot4(go, v10);
             d[4 * j + 3] = dot4(go, v11);
-            float* g00 = gimg + o;
+            ACC* g00 = gimg + o;
             const float c00 = hh * hw * aw, c01 = hh * lw * aw, c10 = lh * hw * aw, c11 = lh * lw * aw;
-            if (m & 1u) atomicAdd(reinterpret_cast<float4*>(g00), make_float4(c00 * go.x, c00 * go.y, c00 * go.z, c00 * go.w));
-            if (m & 2u) atomicAdd(reinterpret_cast<float4*>(g00 + HD), make_float4(c01 * go.x, c01 * go.y, c01 * go.z, c01 * go.w));
-            if (m & 4u) atomicAdd(reinterpret_cast<float4*>(g00 + dy), make_float4(c10 * go.x, c10 * go.y, c10 * go.z, c10 * go.w));
-            if (m & 8u) atomicAdd(reinterpret_cast<float4*>(g00 + dy + HD), make_float4(c11 * go.x, c11 * go.y, c11 * go.z, c11 * go.w));
+            if (m & 1u) scatter4(g00, c00, go, gscale);
+            if (m & 2u) scatter4(g00 + HD, c01, go, gscale);
+            if (m & 4u) scatter4(g00 + dy, c10, go, gscale);
+            if (m & 8u) scatter4(g00 + dy + HD, c11, go, gscale);
           }
         }
       }
       transpose_reduce_4x4<LANES>(d, sub);
       const int mine = c0 + sub / (LANES / 4);
-      if (live && (sub % (LANES / 4)) == 0 && mine < NP) {
+      if (cur.live && (sub % (LANES / 4)) == 0 && mine < NP) {
         const int4 r = s_rec[mine];
         const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
         const float hh = 1.0f - lh, hw = 1.0f - lw;
@@ -392,7 +469,10 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         *reinterpret_cast<float2*>(glp + 2 * mine) = gated ? make_float2(0.f, 0.f) : make_float2(g_x, g_y);
       }
     }
+    if (!has_next) break;
     __syncwarp();   // records are rewritten by the next work item
+    cur = nxt;
+    go = go_next;
   }
 }
 

@@ -80,14 +80,25 @@ __device__ __forceinline__ CT warp_sum(CT v) {
   return v;
 }
 
-// grad_value accumulates in CT (float scratch for bf16 values; the caller converts afterwards).
-template <typename VT, typename CT>
+template <typename CT>
+__device__ __forceinline__ void accumulate(CT* g, CT v, float) { atomicAdd(g, v); }
+__device__ __forceinline__ void accumulate(unsigned long long* g, float v, float scale) {
+  atomicAdd(g, (unsigned long long)__float2ll_rn(v * scale));
+}
+__device__ __forceinline__ void accumulate(unsigned long long* g, double v, float scale) {
+  atomicAdd(g, (unsigned long long)__double2ll_rn(v * (double)scale));
+}
+
+// grad_value accumulates in ACC: CT (float scratch for bf16 values; the caller converts afterwards)
+// or 64-bit fixed point for MSDA_FLAG_DETERMINISTIC.
+template <typename VT, typename CT, typename ACC>
 __global__ void __launch_bounds__(256)
 msda_bwd_generic_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                         const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
-                        const CT* __restrict__ loc, const CT* __restrict__ w, CT* __restrict__ grad_value,
-                        CT* __restrict__ grad_loc, CT* __restrict__ grad_w, int S, int H, int D, int L,
-                        int Q, int P, int64_t rows) {
+                        const CT* __restrict__ loc, const CT* __restrict__ w, ACC* __restrict__ grad_value,
+                        CT* __restrict__ grad_loc, CT* __restrict__ grad_w, const DetScale* __restrict__ det,
+                        int S, int H, int D, int L, int Q, int P, int64_t rows) {
+  const float gscale = det ? det->scale : 1.0f;
   __shared__ CT red[3][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -117,10 +128,10 @@ msda_bwd_generic_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
           const CT top = load_as<CT>(go + c);
           const CT tgv = top * aw;
           CT v1 = 0, v2 = 0, v3 = 0, v4 = 0;
-          if (cell.valid & 1u) { v1 = load_as<CT>(value + o00 + c); atomicAdd(grad_value + o00 + c, hh * hw * tgv); }
-          if (cell.valid & 2u) { v2 = load_as<CT>(value + o00 + dx + c); atomicAdd(grad_value + o00 + dx + c, hh * lw * tgv); }
-          if (cell.valid & 4u) { v3 = load_as<CT>(value + o00 + dy + c); atomicAdd(grad_value + o00 + dy + c, lh * hw * tgv); }
-          if (cell.valid & 8u) { v4 = load_as<CT>(value + o00 + dx + dy + c); atomicAdd(grad_value + o00 + dx + dy + c, lh * lw * tgv); }
+          if (cell.valid & 1u) { v1 = load_as<CT>(value + o00 + c); accumulate(grad_value + o00 + c, hh * hw * tgv, gscale); }
+          if (cell.valid & 2u) { v2 = load_as<CT>(value + o00 + dx + c); accumulate(grad_value + o00 + dx + c, hh * lw * tgv, gscale); }
+          if (cell.valid & 4u) { v3 = load_as<CT>(value + o00 + dy + c); accumulate(grad_value + o00 + dy + c, lh * hw * tgv, gscale); }
+          if (cell.valid & 8u) { v4 = load_as<CT>(value + o00 + dx + dy + c); accumulate(grad_value + o00 + dx + dy + c, lh * lw * tgv, gscale); }
           const CT val = hh * hw * v1 + hh * lw * v2 + lh * hw * v3 + lh * lw * v4;
           s_w += top * val;
           s_x += (hh * (v2 - v1) + lh * (v4 - v3)) * tgv;   // cuh:119-153 grad_w_weight
@@ -150,6 +161,55 @@ msda_bwd_generic_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ 
 __global__ void msda_cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// ---- deterministic mode helpers ------------------------------------------------------------
+// max |x| over a tensor, as the bit pattern of a non-negative float (atomicMax on unsigned is
+// order independent, so the scale -- and with it every bit of the result -- is reproducible).
+template <typename T>
+__global__ void msda_amax_kernel(const T* __restrict__ x, int64_t n, unsigned* __restrict__ out_bits) {
+  float m = 0.0f;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = fabs((double)load_as<typename Compute<T>::type, T>(x + i));
+    if (!(v <= 3.0e38)) bad = true;              // NaN, Inf or beyond float range
+    m = fmaxf(m, __double2float_ru(v));
+  }
+  if (bad) m = __int_as_float(0x7f800000);       // +Inf marks "not finite"
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// scale = 2^k with max|go| * max|w| * 2^k <= 2^38 (double: 2^44); one thread.
+__global__ void msda_det_scale_kernel(const unsigned* __restrict__ amax_bits, DetScale* __restrict__ out, int target_log2) {
+  const float a = __uint_as_float(amax_bits[0]), b = __uint_as_float(amax_bits[1]);
+  const float bound = a * b;
+  DetScale r;
+  if (!(bound < 3.0e38f)) {
+    r.scale = 0.0f;
+    r.inv_scale = __int_as_float(0x7fc00000);    // NaN in, NaN out
+  } else if (bound == 0.0f) {
+    r.scale = 1.0f;
+    r.inv_scale = 1.0f;
+  } else {
+    int e;
+    frexpf(bound, &e);                           // bound = m * 2^e, m in [0.5, 1)  =>  bound < 2^e
+    int k = target_log2 - e;
+    k = k > 120 ? 120 : (k < -120 ? -120 : k);
+    r.scale = ldexpf(1.0f, k);
+    r.inv_scale = ldexpf(1.0f, -k);
+  }
+  *out = r;
+}
+
+// fixed point -> grad_value
+template <typename VT>
+__global__ void msda_det_finalize_kernel(const long long* __restrict__ acc, VT* __restrict__ dst, int64_t n,
+                                         const DetScale* __restrict__ det) {
+  const double inv = (double)det->inv_scale;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    store_as<VT, typename Compute<VT>::type>(dst + i, (typename Compute<VT>::type)((double)acc[i] * inv));
 }
 
 // Test hook, see include/msda.h::msda_debug_bookkeeping.

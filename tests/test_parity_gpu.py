@@ -154,13 +154,14 @@ def test_fast_and_generic_kernels_agree(D, L, P, dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("D,P,threads_knob", [(32, 4, 0), (32, 4, 1), (64, 4, 0), (16, 8, 1), (128, 2, 0), (32, 3, 0)])
 def test_tiled_and_linear_row_orders_agree(D, P, threads_knob, dtype):
-    """Encoder form (Q == S) takes the persistent TILED kernels; forcing LINEAR must give the same
-    forward bit for bit (same per-row arithmetic) and the same gradients up to atomic ordering."""
+    """The opt-in persistent TILED kernels (encoder form, Q == S) must give the same forward as the
+    default LINEAR order bit for bit (same per-row arithmetic) and the same gradients up to atomic
+    ordering."""
     _, _lib, _, workloads, msda_c, _ = _mods()
     levels = [(21, 37), (11, 19), (6, 10), (3, 5)]
     value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 0, 4, D, P, "encoder", "model", 3, value_dtype=dtype)
     go = torch.randn(2, value.shape[1], 4 * D, generator=torch.Generator().manual_seed(1)).to(dtype)
-    tiled = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=threads_knob << 16)
+    tiled = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_ORDER_TILED | (threads_knob << 16))
     linear = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_ORDER_LINEAR)
     assert np.array_equal(tiled[0], linear[0])
     assert np.array_equal(tiled[2], linear[2]) and np.array_equal(tiled[3], linear[3])
@@ -168,6 +169,44 @@ def test_tiled_and_linear_row_orders_agree(D, P, threads_knob, dtype):
     if dtype == torch.float32:
         ref = msda_c.forward(value.numpy(), shapes.numpy(), lsi.numpy(), loc.numpy(), w.numpy(), np.float64)
         assert_close(tiled[0], ref, 1e-5, 1e-6, "tiled out vs oracle")
+
+
+@pytest.mark.parametrize("dtype,D", [(torch.float32, 32), (torch.bfloat16, 32), (torch.float32, 30), (torch.float64, 32),
+                                     (torch.float32, 64)])
+def test_deterministic_backward_is_bit_reproducible(dtype, D):
+    """MSDA_FLAG_DETERMINISTIC (cfg 5's requirement): grad_value identical bit for bit across runs --
+    on a contended shape (many queries onto a tiny map) where float atomics do reorder -- and within
+    tolerance of the fp64 oracle.  grad_loc / grad_w are reproducible in both modes."""
+    _, _lib, _, workloads, msda_c, _ = _mods()
+    levels = [(5, 7), (3, 4), (2, 2)]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 4000, 4, D, 4, "decoder", "model", 21, value_dtype=dtype)
+    go = torch.randn(2, 4000, 4 * D, generator=torch.Generator().manual_seed(2)).to(dtype)
+    runs = [run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_DETERMINISTIC) for _ in range(3)]
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert np.array_equal(a, b)
+    fast = run_cuda(value, shapes, lsi, loc, w, go, dtype)
+    assert np.array_equal(fast[2], runs[0][2]) and np.array_equal(fast[3], runs[0][3])
+    v64 = value.double().numpy()
+    rgv, _, _ = msda_c.backward(go.double().numpy(), v64, shapes.numpy(), lsi.numpy(), loc.numpy(), w.numpy(), np.float64)
+    tol = {torch.float32: 1e-5, torch.bfloat16: 1e-2, torch.float64: 1e-9}[dtype]
+    assert_close(runs[0][1], rgv, tol, 1e-6, "deterministic grad_value vs oracle")
+    assert_close(fast[1], rgv, tol, 1e-6, "atomic grad_value vs oracle")
+
+
+def test_deterministic_backward_scale_extremes():
+    """The fixed-point scale follows max|grad_out| * max|w|: tiny and huge gradients keep ~2^-38 relative
+    resolution; all-zero gradients give exact zeros."""
+    _, _lib, _, workloads, msda_c, _ = _mods()
+    levels = [(5, 7), (3, 4)]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 1, 50, 2, 32, 4, "decoder", "model", 5)
+    go = torch.randn(1, 50, 64, generator=torch.Generator().manual_seed(2))
+    base = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_DETERMINISTIC)[1]
+    for factor in (2.0 ** -60, 2.0 ** 40):
+        got = run_cuda(value, shapes, lsi, loc, w, go * factor, flags=_lib.FLAG_DETERMINISTIC)[1]
+        assert np.array_equal(got, base * factor)          # power-of-two scaling commutes exactly
+    zero = run_cuda(value, shapes, lsi, loc, w, go * 0, flags=_lib.FLAG_DETERMINISTIC)[1]
+    assert not zero.any()
 
 
 # ------------------------------------------------------------------------------------------------
