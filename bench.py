@@ -69,7 +69,8 @@ def config_dict(wl, args, extra=None):
         "heads": wl.num_heads, "head_dim": wl.head_dim, "points": wl.num_points, "value_dtype": wl.value_dtype,
         "points_per_step_per_gpu": wl.points * args.layers, "dist": args.dist,
         "l2_hygiene": "inputs larger than L2: 6 distinct layer input sets (~1.3 GB each) cycled per step",
-        "parallelism": f"image-batch sharding x{args.gpus}, no collective inside the op",
+        "parallelism": f"image-batch sharding x{args.gpus}, no collective inside the op"
+                       + ("; per step one NCCL mean all-reduce of the projection-weight grads (5.5 MB)" if args.gpus > 1 else ""),
     }
     if extra:
         cfg.update(extra)
@@ -133,7 +134,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU baseline (oracle port): rank 0 only, bounded sample
 # --------------------------------------------------------------------------------------------
-def cpu_baseline(wl, dist, iters=3, budget_s=25.0):
+def cpu_baseline(wl, dist, iters=40, budget_s=15.0):
     from oracle import msda_torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -245,8 +246,16 @@ def main():
         go = torch.randn(wl.batch, wl.queries, wl.num_heads * wl.head_dim, device=dev,
                          generator=torch.Generator(device=dev).manual_seed(7 + i)).to(out_dt)
         layers.append((value, shapes, lsi, loc, w, go))
-    # the training config's all-reduce payload: projection-weight grads of the L modules
-    proj_grads = torch.zeros(L * 230272, device=dev) if dist_on else None
+    # the training config's exchange step: mean all-reduce of the L modules' projection-weight grads
+    bucket = None
+    if dist_on:
+        from ir_ads_b200 import MultiScaleDeformableAttention, sharding
+        mods = [MultiScaleDeformableAttention(wl.num_heads * wl.head_dim, wl.num_heads, wl.num_levels,
+                                              wl.num_points).to(dev) for _ in range(L)]
+        params = sharding.projection_parameters(mods)
+        for p in params:
+            p.grad = torch.ones_like(p)
+        bucket = sharding.GradBucket(params)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -264,7 +273,7 @@ def main():
                 record.append((e0, e1, e2))
             del out
         if dist_on:
-            dist.all_reduce(proj_grads)
+            bucket.all_reduce_mean()
 
     def barrier():
         if dist_on:
@@ -298,9 +307,8 @@ def main():
 
     ms_step = ms_total / args.steps
     if dist_on:
-        t = torch.tensor([ms_step], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item())
+        from ir_ads_b200.sharding import max_over_ranks
+        ms_step = max_over_ranks(ms_step, dev)
     value_pts = n_pts_layer * L * world / (ms_step * 1e-3)
 
     # ---------------- e2e: public autograd API, host buffers ----------------
@@ -345,7 +353,10 @@ def main():
 
 
 def run_e2e(wl, layers, dev, dist_on, world, args):
-    """Host buffers in, host buffers out, through MultiScaleDeformableAttnFunction.apply + backward."""
+    """Host buffers in, host buffers out, through MultiScaleDeformableAttnFunction.apply + backward.
+    Three streams (H2D, compute, D2H) so that layer i+1's upload and layer i-1's download overlap layer
+    i's kernels; device input buffers are double-buffered.  Every byte of value / locations / weights /
+    grad_output goes host->device and every byte of output and the three gradients comes back, per layer."""
     import ir_ads_b200
     value, shapes, lsi, loc, w, go = layers[0]
     host_in = [t.cpu().pin_memory() for t in (value, loc, w, go)]
@@ -356,40 +367,59 @@ def run_e2e(wl, layers, dev, dist_on, world, args):
     d2h = sum(t.numel() * t.element_size() for t in host_out)
     L = len(layers)
     steps = max(2, min(args.steps, 5))
+    s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
+    dev_in = [[torch.empty_like(t, device=dev) for t in host_in] for _ in range(2)]
+    ev = lambda: torch.cuda.Event()
+    in_free = [ev(), ev()]      # compute finished reading dev_in[k]
+    for e in in_free:
+        e.record(s_cmp)
 
-    def one_layer():
-        v = host_in[0].to(dev, non_blocking=True).requires_grad_(True)
-        lo = host_in[1].to(dev, non_blocking=True).requires_grad_(True)
-        ww = host_in[2].to(dev, non_blocking=True).requires_grad_(True)
-        g = host_in[3].to(dev, non_blocking=True)
-        out = ir_ads_b200.MultiScaleDeformableAttnFunction.apply(v, shapes, lsi, lo, ww, 64)
-        out.backward(g)
-        host_out[0].copy_(out.detach(), non_blocking=True)
-        host_out[1].copy_(v.grad, non_blocking=True)
-        host_out[2].copy_(lo.grad, non_blocking=True)
-        host_out[3].copy_(ww.grad, non_blocking=True)
+    def run(n_layers):
+        for i in range(n_layers):
+            k = i & 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(in_free[k])
+                for d, h in zip(dev_in[k], host_in):
+                    d.copy_(h, non_blocking=True)
+                ready = ev()
+                ready.record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ready)
+                v = dev_in[k][0].detach().requires_grad_(True)
+                lo = dev_in[k][1].detach().requires_grad_(True)
+                ww = dev_in[k][2].detach().requires_grad_(True)
+                out = ir_ads_b200.MultiScaleDeformableAttnFunction.apply(v, shapes, lsi, lo, ww, 64)
+                out.backward(dev_in[k][3])
+                results = [out.detach(), v.grad, lo.grad, ww.grad]
+                in_free[k] = ev()
+                in_free[k].record(s_cmp)
+                done = ev()
+                done.record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                for h, r in zip(host_out, results):
+                    r.record_stream(s_out)
+                    h.copy_(r, non_blocking=True)
 
-    for _ in range(2):
-        one_layer()
+    run(2)
     if dist_on:
         import torch.distributed as dist
         dist.barrier()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
+    t0.record(s_in)
     for _ in range(steps):
-        for _ in range(L):
-            one_layer()
-    t1.record()
+        run(L)
+    t1.record(s_out)
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / steps
     if dist_on:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        from ir_ads_b200.sharding import max_over_ranks
+        ms = max_over_ranks(ms, dev)
     return {"value": wl.points * L * world / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * L,
             "d2h_bytes_per_step": d2h * L, "ms_per_step": ms, "steps": steps,
-            "path": "pinned host -> H2D -> MultiScaleDeformableAttnFunction.apply + backward -> D2H of out and 3 grads"}
+            "path": "pinned host -> H2D stream -> MultiScaleDeformableAttnFunction.apply + backward -> D2H stream "
+                    "(out + 3 grads), 3-stream pipeline"}
 
 
 def run_ref_cuda(layers, n_pts_layer):

@@ -13,7 +13,7 @@ python bench.py --steps 10 --warmup 3 > "$out/bench_${tag}.json" 2> "$out/bench_
 python bench.py --impl reference --steps 3 --warmup 1 > "$out/bench_ref_${tag}.json" 2> "$out/bench_ref_${tag}.err"
 PROF="python bench.py --steps 1 --warmup 3 --layers 1 --no-cpu-baseline --no-e2e --no-ref-cuda"
 $PROF > "$out/prof_plain_${tag}.log" 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file "$out/launches_${tag}.csv" $PROF > "$out/ncu_launches_${tag}.log" 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file "$out/launches_${tag}.csv" $PROF > "$out/ncu_launches_${tag}.log" 2>&1
 $PROF > "$out/prof_plain2_${tag}.log" 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:msda_ -s 6 -c 2 -f -o "$out/prof_${tag}" $PROF > "$out/ncu_full_${tag}.log" 2>&1
 ls -la "$out"
