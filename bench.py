@@ -210,6 +210,15 @@ def peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload: str, kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[workload].get(kernel)
+    except Exception:
+        return None
+
+
 def main():
     args = parse_args()
     wl = WORKLOADS[args.workload]
@@ -324,15 +333,17 @@ def main():
     if rank == 0:
         peak, peak_src = peak_hbm()
         achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+        bwd_name = _lib.lib().msda_dispatch_name(
+            wl.head_dim, wl.num_levels, wl.num_points, wl.spatial_size, wl.num_heads,
+            _lib.MSDA_BF16 if wl.value_dtype == "bf16" else _lib.MSDA_F32, args.flags, 1).decode()
         line = {
             "metric": METRIC, "value": value_pts, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if wl.value_dtype == "f32" else "bf16(value) + f32 accumulate",
             "data": "synthetic", "config": config_dict(wl, args),
-            "roofline": {"bound": "hbm", "kernel": _lib.lib().msda_dispatch_name(
-                wl.head_dim, wl.num_levels, wl.num_points, wl.spatial_size, wl.num_heads,
-                _lib.MSDA_BF16 if wl.value_dtype == "bf16" else _lib.MSDA_F32, args.flags, 1).decode(),
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": bwd_name,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(wl.name, bwd_name) if args.flags == 0 else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
                 "launch_ms": bwd_ms, "note": "launch_ms includes the grad_value zero-fill memset issued by msda_backward",
                 "fwd": {"algorithmic_bytes_per_launch": fwd_bytes, "launch_ms": fwd_ms,

@@ -78,6 +78,8 @@ extern "C" {
  * tile's gather footprint stays in L1.  Same results; measured slower than LINEAR so far,
  * hence opt-in.  Bits 16-17 are an unstable tuning knob of these kernels (CTA size). */
 #define MSDA_FLAG_ORDER_TILED (1u << 3)
+/* One CTA = a strip of consecutive queries of ONE head (any Q): x-adjacent queries re-use corner lines in L1. */
+#define MSDA_FLAG_ORDER_STRIP (1u << 4)
 
 int msda_abi_version(void);
 

@@ -11,7 +11,8 @@ import subprocess
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmsda_b200.so")
+# MSDA_B200_LIB overrides the library path (kernel-variant experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_PKG, "libmsda_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "msda.h")
 
 # include/msda.h
@@ -21,6 +22,7 @@ FLAG_DETERMINISTIC = 1 << 0
 FLAG_FORCE_GENERIC = 1 << 1
 FLAG_ORDER_LINEAR = 1 << 2
 FLAG_ORDER_TILED = 1 << 3
+FLAG_ORDER_STRIP = 1 << 4
 ABI_VERSION = 1
 
 _lock = threading.Lock()

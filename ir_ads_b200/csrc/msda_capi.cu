@@ -127,20 +127,25 @@ cudaError_t persistent_grid(K kernel, int threads, size_t smem, unsigned* grid) 
 bool use_tiled(const Dims& d, unsigned flags) {
   return d.Q == d.S && (flags & MSDA_FLAG_ORDER_TILED) && !(flags & MSDA_FLAG_ORDER_LINEAR);
 }
+bool use_strip(const Dims& d, unsigned flags) {
+  (void)d;
+  return (flags & MSDA_FLAG_ORDER_STRIP) && !(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED));
+}
 // experiment knob (bits 16-17): CTA size of the TILED kernels; 0 = default
 int tiled_threads(unsigned flags) { return ((flags >> 16) & 3u) == 1u ? 512 : 1024; }
 
-template <int D, typename VT, int PT, int THREADS, bool TILED>
+template <int D, typename VT, int PT, int THREADS, int TILED>
 int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
                     const void* loc, const void* w, void* out) {
   using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
-  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::fwd_row_words(NP) * 4;
+  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::fwd_row_words(NP, TILED == 1) * 4;
   auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
-  if (TILED) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
+  if (TILED == 1) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
+  if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
   k<<<grid, THREADS, smem, st>>>((const VT*)value, shapes, lsi, (const float*)loc, (const float*)w, (VT*)out, d.B,
                                  d.S, d.H, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -148,18 +153,19 @@ int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int
   return MSDA_OK;
 }
 
-template <int D, typename VT, int PT, int THREADS, bool TILED, typename ACC>
+template <int D, typename VT, int PT, int THREADS, int TILED, typename ACC>
 int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
                     const int64_t* lsi, const void* loc, const void* w, ACC* gv, void* gl, void* gw,
                     const msda::DetScale* det) {
   using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
-  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::bwd_row_words(NP) * 4;
+  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::bwd_row_words(NP, TILED == 1) * 4;
   auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
-  if (TILED) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
+  if (TILED == 1) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
+  if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
   k<<<grid, THREADS, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
                                  gv, (float*)gl, (float*)gw, det, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -169,9 +175,10 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
 
 #define MSDA_DISPATCH_ORDER(D_, VT_, PT_, CALL)                                      \
   do {                                                                               \
-    if (!use_tiled(d, flags)) return CALL(D_, VT_, PT_, 256, false);                 \
-    if (tiled_threads(flags) == 512) return CALL(D_, VT_, PT_, 512, true);           \
-    return CALL(D_, VT_, PT_, 1024, true);                                           \
+    if (use_strip(d, flags)) return CALL(D_, VT_, PT_, 256, 2);                      \
+    if (!use_tiled(d, flags)) return CALL(D_, VT_, PT_, 256, 0);                     \
+    if (tiled_threads(flags) == 512) return CALL(D_, VT_, PT_, 512, 1);              \
+    return CALL(D_, VT_, PT_, 1024, 1);                                              \
   } while (0)
 
 #define MSDA_DISPATCH_PT(D_, VT_, CALL)                      \
@@ -203,6 +210,9 @@ int fwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const vo
 int bwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* go, const void* value,
              const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl,
              void* gw) {
+  // default row order of the backward: STRIP (measured 3 % faster than LINEAR at cfg 2: fewer L1 misses
+  // on the crossbar-bound kernel); the forward keeps LINEAR
+  if (!(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED))) flags |= MSDA_FLAG_ORDER_STRIP;
 #define CALL_BWD(D_, VT_, PT_, TH_, TL_) \
   launch_bwd_fast<D_, VT_, PT_, TH_, TL_, float>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw, nullptr)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
@@ -216,7 +226,7 @@ int bwd_fast_det(cudaStream_t st, const Dims& d, int dtype, const void* go, cons
                  const msda::DetScale* det) {
   const unsigned flags = MSDA_FLAG_ORDER_LINEAR;
 #define CALL_BWD(D_, VT_, PT_, TH_, TL_)                                                                      \
-  launch_bwd_fast<D_, VT_, PT_, 256, false, unsigned long long>(st, d, go, value, shapes, lsi, loc, w, acc, gl, \
+  launch_bwd_fast<D_, VT_, PT_, 256, 0, unsigned long long>(st, d, go, value, shapes, lsi, loc, w, acc, gl, \
                                                                 gw, det)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);

@@ -133,14 +133,15 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// shared-memory words per row (host and device must agree)
-__host__ __device__ constexpr int fwd_row_words(int NP) {
-  // float4 cw[NP] | int off[NP] | float2 raw_xy[NP] (8-byte aligned) | float raw_w[NP] | pad
-  return ((((5 * NP + 1) & ~1) + 3 * NP + 3) & ~3) + 4;
+// shared-memory words per row (host and device must agree).  STAGED adds the raw loc/w buffers of
+// the persistent (TILED) kernels' cp.async pipeline.
+__host__ __device__ constexpr int fwd_row_words(int NP, bool staged) {
+  // float4 cw[NP] | int oc[NP] | [float2 raw_xy[NP] (8-byte aligned) | float raw_w[NP]] | pad
+  return (((((5 * NP + 1) & ~1) + (staged ? 3 * NP : 0)) + 3) & ~3) + 4;
 }
-__host__ __device__ constexpr int bwd_row_words(int NP) {
-  // int4 rec[NP] | float2 raw_xy[NP] | float raw_w[NP] | pad
-  return ((7 * NP + 3) & ~3) + 4;
+__host__ __device__ constexpr int bwd_row_words(int NP, bool staged) {
+  // float4 cw[NP] | int4 fin[NP] | [float2 raw_xy[NP] | float raw_w[NP]] | pad
+  return ((8 * NP + (staged ? 3 * NP : 0) + 3) & ~3) + 4;
 }
 
 template <int LANES>
@@ -156,8 +157,11 @@ __device__ __forceinline__ void stage_row(float2* raw_xy, float* raw_w, const fl
   }
 }
 
-// Row iterator: yields this thread's row for every work item of the CTA (grid-stride).
-template <int D, int THREADS, bool TILED>
+// Row iterator: yields this thread's row for every work item of the CTA.
+// ORDER: 0 = LINEAR, 1 = TILED (persistent grid-stride), 2 = STRIP (one CTA = RPC consecutive queries
+// of ONE head; x-adjacent queries of a head share bilinear corners, so the CTA re-uses lines in L1 --
+// needs no knowledge of the level shapes and works for any Q).
+template <int D, int THREADS, int ORDER>
 struct RowWalk {
   using G = Geom<D, THREADS>;
   int64_t item, n_items, rows;
@@ -165,14 +169,26 @@ struct RowWalk {
   __device__ __forceinline__ RowWalk(const LevelTab* tab, int B, int H, int64_t rows_) : rows(rows_) {
     rin = threadIdx.x / G::LANES;
     item = blockIdx.x;
-    n_items = TILED ? (int64_t)B * H * tab->total_tiles : (rows + G::RPC - 1) / G::RPC;
+    if (ORDER == 1) n_items = (int64_t)B * H * tab->total_tiles;
+    else if (ORDER == 2) n_items = (int64_t)B * H * ((rows / ((int64_t)B * H) + G::RPC - 1) / G::RPC);
+    else n_items = (rows + G::RPC - 1) / G::RPC;
   }
   __device__ __forceinline__ bool done() const { return item >= n_items; }
-  // LINEAR kernels are launched with one CTA per item: a single pass, no loop-carried state.
-  __device__ __forceinline__ void next() { item = TILED ? item + gridDim.x : n_items; }
+  // LINEAR / STRIP kernels are launched with one CTA per item: a single pass, no loop-carried state.
+  __device__ __forceinline__ void next() { item = (ORDER == 1) ? item + gridDim.x : n_items; }
   __device__ __forceinline__ RowRef get(const LevelTab* tab, int L, int H, int Q) const {
     RowRef r;
-    if (TILED) {
+    if (ORDER == 2) {
+      const int chunks = (Q + G::RPC - 1) / G::RPC;
+      const int h = (int)(item % H);
+      const int64_t bc = item / H;
+      const int q = (int)(bc % chunks) * G::RPC + rin;
+      const int b = (int)(bc / chunks);
+      r.live = q < Q;
+      r.b = b;
+      r.h = h;
+      r.row = r.live ? ((int64_t)b * Q + q) * H + h : 0;
+    } else if (ORDER == 1) {
       const int h = (int)(item % H);
       const int64_t bt = item / H;
       const int t = (int)(bt % tab->total_tiles);
@@ -200,28 +216,64 @@ struct RowWalk {
   }
 };
 
+// ---- per-point record --------------------------------------------------------------------------
+// Every corner ADDRESS in a record is valid (coordinates clamped into the map), so the gather loop
+// has no predicates, no zero-fills and no branches; zero padding lives in the WEIGHTS (exactly 0 for
+// a padded corner or a gated-out point).  oc = element offset of the clamped low corner inside the
+// image (a multiple of 16) with four flag bits:
+//   bit0  the x+1 corner is a distinct pixel (else it aliases the low one and carries weight 0)
+//   bit1  same for y+1
+//   bit2  x0 inside the map      bit3  y0 inside the map        (backward's finalize step only)
+struct PointRec {
+  float4 cw;   // corner weights (v1..v4 of cuh:56-80) x attention weight, 0 where padded
+  int oc;
+  float lw, lh;  // fractional parts; lw < 0 marks a gated-out point
+};
+
+__device__ __forceinline__ PointRec make_record(float x, float y, float aw, int Hl, int Wl, int start, int H, int h,
+                                                int D) {
+  PointRec r;
+  const Cell<float> c = locate<float>(x, y, Hl, Wl);
+  const float hh = 1.0f - c.lh, hw = 1.0f - c.lw;
+  r.cw.x = (c.valid & 1u) ? hh * hw * aw : 0.0f;
+  r.cw.y = (c.valid & 2u) ? hh * c.lw * aw : 0.0f;
+  r.cw.z = (c.valid & 4u) ? c.lh * hw * aw : 0.0f;
+  r.cw.w = (c.valid & 8u) ? c.lh * c.lw * aw : 0.0f;
+  const bool gated = c.valid == 0u;
+  const bool x0v = c.x0 >= 0, x1v = c.x0 + 1 <= Wl - 1, y0v = c.y0 >= 0, y1v = c.y0 + 1 <= Hl - 1;
+  const int xc = gated ? 0 : max(c.x0, 0), yc = gated ? 0 : max(c.y0, 0);
+  int flags = 0;
+  if (!gated) flags = (int)(x0v && x1v) | ((int)(y0v && y1v) << 1) | ((int)x0v << 2) | ((int)y0v << 3);
+  r.oc = (((start + yc * Wl + xc) * H + h) * D) | flags;
+  r.lw = gated ? -1.0f : c.lw;
+  r.lh = c.lh;
+  return r;
+}
+
 // =============================================================================================
 // Forward
 // =============================================================================================
-// Software pipeline per warp (persistent TILED CTAs; LINEAR runs it once):
-//   wait for this item's raw loc/w in shared memory  ->  phase 1: records  ->  issue cp.async for
-//   the NEXT item's loc/w  ->  phase 2: gather (the long phase, hides the HBM latency of the copy).
-// records per row: float4 cw[NP] (corner weights x attention weight, 0 for padded corners),
-//                  int off[NP]   (element offset of corner (y0,x0) of this head inside the image,
-//                                 multiple of 16; low 4 bits = corner validity)
-template <int D, typename VT, int PT, int THREADS, bool TILED>
-__global__ void __launch_bounds__(THREADS, (THREADS == 512) ? 3 : 1)
+// LINEAR / STRIP: one pass per CTA, phase 1 reads loc/w straight from global memory.
+// TILED (persistent): software pipeline per warp -- wait for this item's raw loc/w in shared memory
+//   -> phase 1: records -> issue cp.async for the NEXT item's loc/w -> phase 2: gather (the long
+//   phase, hides the HBM latency of the copy).
+template <int D, typename VT, int PT, int THREADS, int ORDER>
+#ifndef MSDA_FWD_MINB
+#define MSDA_FWD_MINB 6
+#endif
+__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_FWD_MINB : ((THREADS == 512) ? 3 : 1))
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ w, VT* __restrict__ out, int B, int S, int H, int L, int Q,
                      int P, int64_t rows) {
   using G = Geom<D, THREADS>;
   constexpr int LANES = G::LANES;
+  constexpr bool STAGED = (ORDER == 1);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
-  const int row_words = fwd_row_words(NP);
+  const int row_words = fwd_row_words(NP, STAGED);
 
   load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
 
@@ -230,63 +282,59 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   const int HD = H * D;
   float* my = recs + (size_t)rin * row_words;
   float4* s_cw = reinterpret_cast<float4*>(my);
-  int* s_off = reinterpret_cast<int*>(my + 4 * NP);
+  int* s_oc = reinterpret_cast<int*>(my + 4 * NP);
   float2* raw_xy = reinterpret_cast<float2*>(my + ((5 * NP + 1) & ~1));
   float* raw_w = my + ((5 * NP + 1) & ~1) + 2 * NP;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  RowWalk<D, THREADS, TILED> walk(tab, B, H, rows);
+  RowWalk<D, THREADS, ORDER> walk(tab, B, H, rows);
   if (walk.done()) return;
   RowRef cur = walk.get(tab, L, H, Q);
-  stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
+  if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
   while (true) {
     walk.next();
     const bool has_next = !walk.done();
     RowRef nxt = cur;
     if (has_next) nxt = walk.get(tab, L, H, Q);
-    cp_async_wait_all();
-    __syncwarp();
+    if (STAGED) {
+      cp_async_wait_all();
+      __syncwarp();
+    }
     // ---- phase 1: records ----
     if (cur.live) {
+      const float2* lp = reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2);
+      const float* wp = w + cur.row * (int64_t)NP;
       for (int pt = sub; pt < NP; pt += LANES) {
-        const float2 xy = raw_xy[pt];
-        const float aw = raw_w[pt];
+        const float2 xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
+        const float aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
         const int l = level_of<PT>(pt, P);
-        const int Hl = tab->H[l], Wl = tab->W[l];
-        const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
-        const float hh = 1.0f - c.lh, hw = 1.0f - c.lw;
-        float4 cw;
-        cw.x = (c.valid & 1u) ? hh * hw * aw : 0.0f;
-        cw.y = (c.valid & 2u) ? hh * c.lw * aw : 0.0f;
-        cw.z = (c.valid & 4u) ? c.lh * hw * aw : 0.0f;
-        cw.w = (c.valid & 8u) ? c.lh * c.lw * aw : 0.0f;
-        const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + cur.h) * D;
-        s_cw[pt] = cw;
-        s_off[pt] = o | (int)c.valid;
+        const PointRec r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+        s_cw[pt] = r.cw;
+        s_oc[pt] = r.oc;
       }
     }
     __syncwarp();
-    if (has_next) stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
+    if (STAGED && has_next) stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
 
     // ---- phase 2: gather ----
     if (cur.live) {
       const VT* vimg = value + (int64_t)cur.b * S * HD + sub * 4;
-      float4 acc = zero;
+      asm volatile("" : "+l"(vimg));   // keep the row base as ONE 64-bit register: corner address = base + off*4 (IMAD.WIDE)
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       int pt = 0;
       for (int l = 0; l < L; ++l) {
-        const int dy = tab->W[l] * HD;
+        const int dyl = tab->W[l] * HD;
         const int np = (PT > 0) ? PT : P;
 #pragma unroll
         for (int p = 0; p < np; ++p, ++pt) {
-          const int oc = s_off[pt];
-          const unsigned m = (unsigned)oc & 15u;
-          if (m == 0u) continue;
+          const int oc = s_oc[pt];
           const float4 cw = s_cw[pt];
-          const VT* p00 = vimg + (oc & ~15);
-          const float4 v00 = (m & 1u) ? ld4(p00) : zero;
-          const float4 v01 = (m & 2u) ? ld4(p00 + HD) : zero;
-          const float4 v10 = (m & 4u) ? ld4(p00 + dy) : zero;
-          const float4 v11 = (m & 8u) ? ld4(p00 + dy + HD) : zero;
+          const int o00 = oc & ~15;
+          const int o01 = o00 + ((oc & 1) ? HD : 0);
+          const int dy = (oc & 2) ? dyl : 0;
+          const float4 v00 = ld4(vimg + o00);
+          const float4 v01 = ld4(vimg + o01);
+          const float4 v10 = ld4(vimg + (o00 + dy));
+          const float4 v11 = ld4(vimg + (o01 + dy));
           fma4(acc, cw.x, v00);
           fma4(acc, cw.y, v01);
           fma4(acc, cw.z, v10);
@@ -304,19 +352,49 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 // =============================================================================================
 // Backward
 // =============================================================================================
-// records per row: int4 rec[NP] = { off | valid, lw, lh, aw } (floats bit-cast)
+// records per row: float4 cw[NP] (as forward) | int4 fin[NP] = { oc, lw, lh, aw } (floats bit-cast)
 //
 // grad_value accumulation: float (vector red, fast, order-dependent rounding) or, for
 // MSDA_FLAG_DETERMINISTIC, 64-bit fixed point (integer red: the sum is order independent).
 __device__ __forceinline__ void scatter4(float* g, const float c, const float4 go, float /*scale*/) {
-  atomicAdd(reinterpret_cast<float4*>(g), make_float4(c * go.x, c * go.y, c * go.z, c * go.w));
+  // red (no return value) on purpose: atomicAdd(float4*) may compile to ATOM.E.ADD.F32x4 with a dead
+  // destination, which pays the return trip; inline PTX pins SASS REDG.E.ADD.F32x4.
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(c * go.x), "f"(c * go.y), "f"(c * go.z),
+               "f"(c * go.w)
+               : "memory");
 }
-__device__ __forceinline__ void scatter4(unsigned long long* g, const float c, const float4 go, float scale) {
-  // c*go is rounded to float exactly as in the float path, then scaled by a power of two (exact)
-  atomicAdd(g + 0, (unsigned long long)__float2ll_rn((c * go.x) * scale));
-  atomicAdd(g + 1, (unsigned long long)__float2ll_rn((c * go.y) * scale));
-  atomicAdd(g + 2, (unsigned long long)__float2ll_rn((c * go.z) * scale));
-  atomicAdd(g + 3, (unsigned long long)__float2ll_rn((c * go.w) * scale));
+// Deterministic flavour: `go` holds the TRANSPOSED channels (component i = channel i*LANES + sub, see
+// transpose_channels), and g already points at channel `sub`, so the LANES lanes of a row write 8*LANES
+// contiguous bytes per instruction: every 32-byte sector receives one full-width 64-bit red per lane
+// instead of four partial ones (there is no vector form of the 64-bit integer red).
+template <int LANES>
+__device__ __forceinline__ void scatter4_det(unsigned long long* g, const float c, const float4 go, float scale) {
+  // c*go is rounded to float, then scaled by a power of two (exact) and rounded to an integer
+  atomicAdd(g + 0 * LANES, (unsigned long long)__float2ll_rn((c * go.x) * scale));
+  atomicAdd(g + 1 * LANES, (unsigned long long)__float2ll_rn((c * go.y) * scale));
+  atomicAdd(g + 2 * LANES, (unsigned long long)__float2ll_rn((c * go.z) * scale));
+  atomicAdd(g + 3 * LANES, (unsigned long long)__float2ll_rn((c * go.w) * scale));
+}
+
+// lane `sub` owns channels 4*sub..4*sub+3 in v; returns channels {sub, LANES+sub, 2*LANES+sub, 3*LANES+sub}
+template <int LANES>
+__device__ __forceinline__ float4 transpose_channels(const float4 v, int sub) {
+  const int comp = sub & 3;
+  // channel i*LANES + sub lives in lane (i*LANES + sub)/4, component sub%4; every lane must publish the
+  // component its READERS want, which is the reader's sub%4 -- so do it in 4 rounds, one per component
+  float4 r;
+  float got[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int src = (i * LANES + sub) >> 2;
+    const float c0 = __shfl_sync(0xffffffffu, v.x, src, LANES);
+    const float c1 = __shfl_sync(0xffffffffu, v.y, src, LANES);
+    const float c2 = __shfl_sync(0xffffffffu, v.z, src, LANES);
+    const float c3 = __shfl_sync(0xffffffffu, v.w, src, LANES);
+    got[i] = comp == 0 ? c0 : (comp == 1 ? c1 : (comp == 2 ? c2 : c3));
+  }
+  r.x = got[0]; r.y = got[1]; r.z = got[2]; r.w = got[3];
+  return r;
 }
 
 template <int LANES>
@@ -348,8 +426,11 @@ __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
   }
 }
 
-template <int D, typename VT, int PT, int THREADS, bool TILED, typename ACC>
-__global__ void __launch_bounds__(THREADS)
+#ifndef MSDA_BWD_MINB
+#define MSDA_BWD_MINB 1
+#endif
+template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC>
+__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_BWD_MINB : 1)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ w,
@@ -358,11 +439,12 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                      int Q, int P, int64_t rows) {
   using G = Geom<D, THREADS>;
   constexpr int LANES = G::LANES;
+  constexpr bool STAGED = (ORDER == 1);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
-  const int row_words = bwd_row_words(NP);
+  const int row_words = bwd_row_words(NP, STAGED);
 
   load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
 
@@ -370,53 +452,61 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   const int rin = threadIdx.x / LANES;
   const int HD = H * D;
   float* my = recs + (size_t)rin * row_words;
-  int4* s_rec = reinterpret_cast<int4*>(my);
-  float2* raw_xy = reinterpret_cast<float2*>(my + 4 * NP);
-  float* raw_w = my + 6 * NP;
+  float4* s_cw = reinterpret_cast<float4*>(my);
+  int4* s_fin = reinterpret_cast<int4*>(my + 4 * NP);
+  float2* raw_xy = reinterpret_cast<float2*>(my + 8 * NP);
+  float* raw_w = my + 10 * NP;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   const float gscale = det ? det->scale : 1.0f;
 
   // A warp stays converged for the full-mask shuffles below: rows that do not exist (edge tiles,
-  // the tail of the last CTA) have every point marked invalid, so they load nothing, scatter
-  // nothing and never write.
-  RowWalk<D, THREADS, TILED> walk(tab, B, H, rows);
+  // the tail of the last CTA) get all-zero weights, so they scatter nothing and never write.
+  RowWalk<D, THREADS, ORDER> walk(tab, B, H, rows);
   if (walk.done()) return;
   RowRef cur = walk.get(tab, L, H, Q);
-  stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
+  if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
   float4 go = cur.live ? ld4(grad_out + cur.row * D + sub * 4) : zero;
   while (true) {
     walk.next();
     const bool has_next = !walk.done();
     RowRef nxt = cur;
     if (has_next) nxt = walk.get(tab, L, H, Q);
-    cp_async_wait_all();
-    __syncwarp();
-    for (int pt = sub; pt < NP; pt += LANES) {
-      int4 r = make_int4(0, 0, 0, 0);
-      if (cur.live) {
-        const float2 xy = raw_xy[pt];
-        const float aw = raw_w[pt];
-        const int l = level_of<PT>(pt, P);
-        const int Hl = tab->H[l], Wl = tab->W[l];
-        const Cell<float> c = locate<float>(xy.x, xy.y, Hl, Wl);
-        const int o = ((tab->start[l] + c.y0 * Wl + c.x0) * H + cur.h) * D;
-        r.x = o | (int)c.valid;
-        r.y = __float_as_int(c.lw);
-        r.z = __float_as_int(c.lh);
-        r.w = __float_as_int(aw);
+    if (STAGED) {
+      cp_async_wait_all();
+      __syncwarp();
+    }
+    {
+      const float2* lp = reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2);
+      const float* wp = w + cur.row * (int64_t)NP;
+      for (int pt = sub; pt < NP; pt += LANES) {
+        float4 cw = zero;
+        int4 fin = make_int4(0, __float_as_int(-1.0f), 0, 0);
+        if (cur.live) {
+          const float2 xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
+          const float aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
+          const int l = level_of<PT>(pt, P);
+          const PointRec r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+          cw = r.cw;
+          fin = make_int4(r.oc, __float_as_int(r.lw), __float_as_int(r.lh), __float_as_int(aw));
+        }
+        s_cw[pt] = cw;
+        s_fin[pt] = fin;
       }
-      s_rec[pt] = r;
     }
     __syncwarp();
     float4 go_next = zero;
     if (has_next) {
-      stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
+      if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
       if (nxt.live) go_next = ld4(grad_out + nxt.row * D + sub * 4);
     }
 
+    constexpr bool DET = sizeof(ACC) == 8;
     const int64_t img = (int64_t)cur.b * S * HD + sub * 4;
     const VT* vimg = value + img;
-    ACC* gimg = grad_value + img;
+    ACC* gimg = grad_value + (DET ? img - sub * 3 : img);   // DET: lane offset is `sub`, not 4*sub
+    asm volatile("" : "+l"(vimg), "+l"(gimg));
+    float4 go_s = go;                                        // what the scatter multiplies
+    if constexpr (DET) go_s = transpose_channels<LANES>(go, sub);   // one 64-bit register each: address = base + off*size (IMAD.WIDE)
     float* glp = grad_loc + cur.row * (int64_t)NP * 2;
     float* gwp = grad_w + cur.row * (int64_t)NP;
 
@@ -425,48 +515,57 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int pt = c0 + j;
-        d[4 * j + 0] = 0.f; d[4 * j + 1] = 0.f; d[4 * j + 2] = 0.f; d[4 * j + 3] = 0.f;
         if (pt < NP) {
-          const int4 r = s_rec[pt];
-          const unsigned m = (unsigned)r.x & 15u;
-          if (m != 0u) {
-            const int l = level_of<PT>(pt, P);
-            const int dy = tab->W[l] * HD;
-            const int o = r.x & ~15;
-            const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
-            const float hh = 1.0f - lh, hw = 1.0f - lw;
-            const VT* p00 = vimg + o;
-            const float4 v00 = (m & 1u) ? ld4(p00) : zero;
-            const float4 v01 = (m & 2u) ? ld4(p00 + HD) : zero;
-            const float4 v10 = (m & 4u) ? ld4(p00 + dy) : zero;
-            const float4 v11 = (m & 8u) ? ld4(p00 + dy + HD) : zero;
-            d[4 * j + 0] = dot4(go, v00);
-            d[4 * j + 1] = dot4(go, v01);
-            d[4 * j + 2] = dot4(go, v10);
-            d[4 * j + 3] = dot4(go, v11);
-            ACC* g00 = gimg + o;
-            const float c00 = hh * hw * aw, c01 = hh * lw * aw, c10 = lh * hw * aw, c11 = lh * lw * aw;
-            if (m & 1u) scatter4(g00, c00, go, gscale);
-            if (m & 2u) scatter4(g00 + HD, c01, go, gscale);
-            if (m & 4u) scatter4(g00 + dy, c10, go, gscale);
-            if (m & 8u) scatter4(g00 + dy + HD, c11, go, gscale);
+          const int oc = s_fin[pt].x;
+          const float4 cw = s_cw[pt];
+          const int l = level_of<PT>(pt, P);
+          const int o00 = oc & ~15;
+          const int o01 = o00 + ((oc & 1) ? HD : 0);
+          const int dy = (oc & 2) ? tab->W[l] * HD : 0;
+          const int o10 = o00 + dy, o11 = o01 + dy;
+          const float4 v00 = ld4(vimg + o00);
+          const float4 v01 = ld4(vimg + o01);
+          const float4 v10 = ld4(vimg + o10);
+          const float4 v11 = ld4(vimg + o11);
+          d[4 * j + 0] = dot4(go, v00);
+          d[4 * j + 1] = dot4(go, v01);
+          d[4 * j + 2] = dot4(go, v10);
+          d[4 * j + 3] = dot4(go, v11);
+          if constexpr (DET) {
+            if (cw.x != 0.0f) scatter4_det<LANES>(gimg + o00, cw.x, go_s, gscale);
+            if (cw.y != 0.0f) scatter4_det<LANES>(gimg + o01, cw.y, go_s, gscale);
+            if (cw.z != 0.0f) scatter4_det<LANES>(gimg + o10, cw.z, go_s, gscale);
+            if (cw.w != 0.0f) scatter4_det<LANES>(gimg + o11, cw.w, go_s, gscale);
+          } else {
+            if (cw.x != 0.0f) scatter4(gimg + o00, cw.x, go_s, gscale);
+            if (cw.y != 0.0f) scatter4(gimg + o01, cw.y, go_s, gscale);
+            if (cw.z != 0.0f) scatter4(gimg + o10, cw.z, go_s, gscale);
+            if (cw.w != 0.0f) scatter4(gimg + o11, cw.w, go_s, gscale);
           }
+        } else {
+          d[4 * j + 0] = 0.f; d[4 * j + 1] = 0.f; d[4 * j + 2] = 0.f; d[4 * j + 3] = 0.f;
         }
       }
       transpose_reduce_4x4<LANES>(d, sub);
       const int mine = c0 + sub / (LANES / 4);
       if (cur.live && (sub % (LANES / 4)) == 0 && mine < NP) {
-        const int4 r = s_rec[mine];
+        const int4 r = s_fin[mine];
         const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
-        const float hh = 1.0f - lh, hw = 1.0f - lw;
-        const int l = level_of<PT>(mine, P);
-        // d[k] = <grad_out, v_k> with padded corners contributing 0 (cuh:119-158)
-        const float g_aw = hh * hw * d[0] + hh * lw * d[1] + lh * hw * d[2] + lh * lw * d[3];
-        const float g_x = (hh * (d[1] - d[0]) + lh * (d[3] - d[2])) * aw * (float)tab->W[l];
-        const float g_y = (hw * (d[2] - d[0]) + lw * (d[3] - d[1])) * aw * (float)tab->H[l];
-        const bool gated = ((unsigned)r.x & 15u) == 0u;   // reference leaves a gated point's grads at 0 (cuh:369)
-        gwp[mine] = gated ? 0.0f : g_aw;
-        *reinterpret_cast<float2*>(glp + 2 * mine) = gated ? make_float2(0.f, 0.f) : make_float2(g_x, g_y);
+        float g_aw = 0.0f, g_x = 0.0f, g_y = 0.0f;      // a gated point's grads stay 0 (cuh:369)
+        if (lw >= 0.0f) {
+          const bool x0v = (r.x & 4) != 0, y0v = (r.x & 8) != 0;
+          const bool x1v = (r.x & 1) != 0 || !x0v, y1v = (r.x & 2) != 0 || !y0v;
+          // d[k] = <grad_out, v_k>; padded corners contribute 0 (cuh:119-158)
+          const float d0 = (x0v && y0v) ? d[0] : 0.0f, d1 = (x1v && y0v) ? d[1] : 0.0f;
+          const float d2 = (x0v && y1v) ? d[2] : 0.0f, d3 = (x1v && y1v) ? d[3] : 0.0f;
+          const float hh = 1.0f - lh, hw = 1.0f - lw;
+          const int l = level_of<PT>(mine, P);
+          g_aw = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;
+          g_x = (hh * (d1 - d0) + lh * (d3 - d2)) * aw * (float)tab->W[l];
+          g_y = (hw * (d2 - d0) + lw * (d3 - d1)) * aw * (float)tab->H[l];
+        }
+        gwp[mine] = g_aw;
+        *reinterpret_cast<float2*>(glp + 2 * mine) = make_float2(g_x, g_y);
       }
     }
     if (!has_next) break;

@@ -80,6 +80,7 @@ class Workload:
 WORKLOADS = {
     "cfg1": Workload("cfg1", tuple(LEVELS["cfg1"]), batch=2, num_query=300, kind="decoder"),
     "cfg2": Workload("cfg2", tuple(LEVELS["dino_r50"]), batch=8, num_query=0, kind="encoder"),
+    "cfg2_bf16": Workload("cfg2_bf16", tuple(LEVELS["dino_r50"]), batch=8, num_query=0, kind="encoder", value_dtype="bf16"),
     "cfg3": Workload("cfg3", tuple(LEVELS["dino_r50"]), batch=8, num_query=2000, kind="decoder", value_dtype="bf16"),
     "cfg3_f32": Workload("cfg3_f32", tuple(LEVELS["dino_r50"]), batch=8, num_query=2000, kind="decoder"),
     "cfg4": Workload("cfg4", tuple(LEVELS["voc"]), batch=2, num_query=0, kind="encoder"),
