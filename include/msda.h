@@ -103,6 +103,35 @@ int msda_backward(void* stream, const void* grad_output, const void* value,
                   void* workspace, size_t workspace_bytes, int dtype, unsigned flags);
 
 /*
+ * Fused module path (an extension, the reference has no counterpart): the
+ * softmax over L*P and the sampling-location arithmetic of MultiScaleDeformableAttention.forward
+ * (/root/reference/detrex/layers/multi_scale_deform_attn.py:300-332) run inside the kernels, so
+ * sampling_locations / attention_weights and their gradients never exist in HBM.
+ *   sampling_offsets  [B, Q, H, L, P, 2] float  raw output of the module's sampling_offsets Linear
+ *   attn_logits       [B, Q, H, L*P]     float  raw output of its attention_weights Linear (pre-softmax)
+ *   reference_points  [B, Q, L, ref_dim] float  ref_dim 2: loc = ref + off / (W_l, H_l)   (py:320-324)
+ *                                               ref_dim 4: loc = ref_xy + off / P * ref_wh * 0.5 (py:326-332)
+ * Backward returns grad_value plus the gradients w.r.t. the two RAW tensors (what the Linear layers'
+ * backward consumes); it uses the same workspace rule as msda_backward.  Only the fast kernels have
+ * a fused form: otherwise MSDA_ERR_UNSUPPORTED is returned (query with msda_fused_supported) and the
+ * caller composes softmax / affine itself around msda_forward / msda_backward.
+ */
+int msda_fused_supported(int channels, int num_levels, int num_point, int spatial_size, int num_heads,
+                         int dtype, unsigned flags);
+int msda_fused_forward(void* stream, const void* value, const int64_t* spatial_shapes,
+                       const int64_t* level_start_index, const float* sampling_offsets,
+                       const float* attn_logits, const float* reference_points, int ref_dim, int batch,
+                       int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                       int num_point, void* output, int dtype, unsigned flags);
+int msda_fused_backward(void* stream, const void* grad_output, const void* value,
+                        const int64_t* spatial_shapes, const int64_t* level_start_index,
+                        const float* sampling_offsets, const float* attn_logits,
+                        const float* reference_points, int ref_dim, int batch, int spatial_size,
+                        int num_heads, int channels, int num_levels, int num_query, int num_point,
+                        void* grad_value, float* grad_offsets, float* grad_logits, void* workspace,
+                        size_t workspace_bytes, int dtype, unsigned flags);
+
+/*
  * Test hook: the integer bookkeeping the float kernels derive from every sampling point.
  *   corner_offsets [B*Q*H*L*P, 4] int64  flat element offset (channel 0) of the four bilinear
  *                  corners inside `value`, -1 for a zero-padded corner or a gated-out point;

@@ -55,6 +55,13 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_backward_workspace_bytes.argtypes = [i, i, i, i, i, i, i, i, u]
     lib.msda_backward.restype = i
     lib.msda_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, vp, vp, sz, i, u]
+    lib.msda_fused_supported.restype = i
+    lib.msda_fused_supported.argtypes = [i, i, i, i, i, i, u]
+    lib.msda_fused_forward.restype = i
+    lib.msda_fused_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp, i, u]
+    lib.msda_fused_backward.restype = i
+    lib.msda_fused_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, sz,
+                                        i, u]
     lib.msda_debug_bookkeeping.restype = i
     lib.msda_debug_bookkeeping.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]
     lib.msda_status_string.restype = ctypes.c_char_p

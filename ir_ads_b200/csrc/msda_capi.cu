@@ -134,40 +134,40 @@ bool use_strip(const Dims& d, unsigned flags) {
 // experiment knob (bits 16-17): CTA size of the TILED kernels; 0 = default
 int tiled_threads(unsigned flags) { return ((flags >> 16) & 3u) == 1u ? 512 : 1024; }
 
-template <int D, typename VT, int PT, int THREADS, int TILED>
+template <int D, typename VT, int PT, int THREADS, int TILED, bool FUSED = false>
 int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
-                    const void* loc, const void* w, void* out) {
+                    const void* loc, const void* w, void* out, msda::FusedArgs fa = msda::FusedArgs{nullptr, 0, 0.f}) {
   using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
   const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::fwd_row_words(NP, TILED == 1) * 4;
-  auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED>;
+  auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED, FUSED>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
   if (TILED == 1) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
   if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
-  k<<<grid, THREADS, smem, st>>>((const VT*)value, shapes, lsi, (const float*)loc, (const float*)w, (VT*)out, d.B,
-                                 d.S, d.H, d.L, d.Q, d.P, rows);
+  k<<<grid, THREADS, smem, st>>>((const VT*)value, shapes, lsi, (const float*)loc, (const float*)w, (VT*)out, fa,
+                                 d.B, d.S, d.H, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
 }
 
-template <int D, typename VT, int PT, int THREADS, int TILED, typename ACC>
+template <int D, typename VT, int PT, int THREADS, int TILED, typename ACC, bool FUSED = false>
 int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
                     const int64_t* lsi, const void* loc, const void* w, ACC* gv, void* gl, void* gw,
-                    const msda::DetScale* det) {
+                    const msda::DetScale* det, msda::FusedArgs fa = msda::FusedArgs{nullptr, 0, 0.f}) {
   using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
   const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::bwd_row_words(NP, TILED == 1) * 4;
-  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC>;
+  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC, FUSED>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
   if (TILED == 1) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
   if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
   k<<<grid, THREADS, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
-                                 gv, (float*)gl, (float*)gw, det, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
+                                 gv, (float*)gl, (float*)gw, det, fa, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
@@ -231,6 +231,43 @@ int bwd_fast_det(cudaStream_t st, const Dims& d, int dtype, const void* go, cons
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
 #undef CALL_BWD
+}
+
+// fused pre-op chain: single-pass row orders only (LINEAR forward, STRIP backward)
+#define MSDA_DISPATCH_PT_FUSED(D_, VT_, CALL)     \
+  do {                                            \
+    if (d.P == 4) return CALL(D_, VT_, 4);        \
+    if (d.P == 8) return CALL(D_, VT_, 8);        \
+    return CALL(D_, VT_, 0);                      \
+  } while (0)
+#define MSDA_DISPATCH_D_FUSED(VT_, CALL)                     \
+  do {                                                       \
+    switch (d.D) {                                           \
+      case 16: MSDA_DISPATCH_PT_FUSED(16, VT_, CALL);        \
+      case 32: MSDA_DISPATCH_PT_FUSED(32, VT_, CALL);        \
+      case 64: MSDA_DISPATCH_PT_FUSED(64, VT_, CALL);        \
+      case 128: MSDA_DISPATCH_PT_FUSED(128, VT_, CALL);      \
+      default: return fail(MSDA_ERR_UNSUPPORTED, "fused path: D=%d", d.D); \
+    }                                                        \
+  } while (0)
+
+int fwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
+              const void* off, const void* logits, void* out, msda::FusedArgs fa) {
+#define CALL_FF(D_, VT_, PT_) launch_fwd_fast<D_, VT_, PT_, 256, 0, true>(st, d, value, shapes, lsi, off, logits, out, fa)
+  if (dtype == MSDA_F32) MSDA_DISPATCH_D_FUSED(float, CALL_FF);
+  MSDA_DISPATCH_D_FUSED(__nv_bfloat16, CALL_FF);
+#undef CALL_FF
+}
+
+int bwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
+              const int64_t* lsi, const void* off, const void* logits, float* gv, void* goff, void* glog,
+              msda::FusedArgs fa) {
+#define CALL_FB(D_, VT_, PT_)                                                                                    \
+  launch_bwd_fast<D_, VT_, PT_, 256, 2, float, true>(st, d, go, value, shapes, lsi, off, logits, gv, goff, glog, \
+                                                     nullptr, fa)
+  if (dtype == MSDA_F32) MSDA_DISPATCH_D_FUSED(float, CALL_FB);
+  MSDA_DISPATCH_D_FUSED(__nv_bfloat16, CALL_FB);
+#undef CALL_FB
 }
 
 // ------------------------------------------------------------------------------------------
@@ -454,6 +491,74 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
     msda::msda_cast_f32_to_bf16_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
         gv32, static_cast<__nv_bfloat16*>(grad_value), n);
     count();
+    MSDA_CUDA(cudaGetLastError());
+  }
+  return MSDA_OK;
+}
+
+int msda_fused_supported(int channels, int num_levels, int num_point, int spatial_size, int num_heads, int dtype,
+                         unsigned flags) {
+  const Dims d{1, spatial_size, num_heads, channels, num_levels, 1, num_point};
+  return fast_ok(d, dtype, flags) && !(flags & MSDA_FLAG_DETERMINISTIC) ? 1 : 0;
+}
+
+int msda_fused_forward(void* stream, const void* value, const int64_t* spatial_shapes,
+                       const int64_t* level_start_index, const float* sampling_offsets, const float* attn_logits,
+                       const float* reference_points, int ref_dim, int batch, int spatial_size, int num_heads,
+                       int channels, int num_levels, int num_query, int num_point, void* output, int dtype,
+                       unsigned flags) {
+  g_err[0] = 0;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  if (int s = check_dims(d, dtype)) return s;
+  if (ref_dim != 2 && ref_dim != 4) return fail(MSDA_ERR_INVALID_ARGUMENT, "ref_dim must be 2 or 4, got %d", ref_dim);
+  if (d.rows() * d.D == 0) return MSDA_OK;
+  if (!msda_fused_supported(channels, num_levels, num_point, spatial_size, num_heads, dtype, flags) || d.S == 0)
+    return fail(MSDA_ERR_UNSUPPORTED, "fused path needs D in {16,32,64,128}, float/bf16 value, L<=16, 1<=L*P<=64");
+  if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !reference_points ||
+      !output)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  DeviceGuard guard;
+  MSDA_CUDA(guard.enter(value));
+  const msda::FusedArgs fa{reference_points, ref_dim, 1.0f / (float)num_point};
+  return fwd_fused(static_cast<cudaStream_t>(stream), d, dtype, value, spatial_shapes, level_start_index,
+                   sampling_offsets, attn_logits, output, fa);
+}
+
+int msda_fused_backward(void* stream, const void* grad_output, const void* value, const int64_t* spatial_shapes,
+                        const int64_t* level_start_index, const float* sampling_offsets, const float* attn_logits,
+                        const float* reference_points, int ref_dim, int batch, int spatial_size, int num_heads,
+                        int channels, int num_levels, int num_query, int num_point, void* grad_value,
+                        float* grad_offsets, float* grad_logits, void* workspace, size_t workspace_bytes, int dtype,
+                        unsigned flags) {
+  g_err[0] = 0;
+  const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  if (int s = check_dims(d, dtype)) return s;
+  if (ref_dim != 2 && ref_dim != 4) return fail(MSDA_ERR_INVALID_ARGUMENT, "ref_dim must be 2 or 4, got %d", ref_dim);
+  if (!msda_fused_supported(channels, num_levels, num_point, spatial_size, num_heads, dtype, flags) ||
+      d.n_value() == 0 || d.n_points() == 0)
+    return fail(MSDA_ERR_UNSUPPORTED, "fused path needs a non-empty problem, D in {16,32,64,128}, float/bf16 value");
+  if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits ||
+      !reference_points || !grad_value || !grad_offsets || !grad_logits)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceGuard guard;
+  MSDA_CUDA(guard.enter(value));
+  const size_t need = msda_backward_workspace_bytes(batch, spatial_size, num_heads, channels, num_levels, num_query,
+                                                    num_point, dtype, flags);
+  if (need && (!workspace || workspace_bytes < need))
+    return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, workspace_bytes);
+  float* gv32 = static_cast<float*>(grad_value);
+  if (dtype == MSDA_BF16) gv32 = static_cast<float*>(workspace);
+  MSDA_CUDA(cudaMemsetAsync(gv32, 0, (size_t)d.n_value() * sizeof(float), st));
+  const msda::FusedArgs fa{reference_points, ref_dim, 1.0f / (float)num_point};
+  if (int s = bwd_fused(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_offsets,
+                        attn_logits, gv32, grad_offsets, grad_logits, fa))
+    return s;
+  if (dtype == MSDA_BF16) {
+    const int64_t n = d.n_value();
+    msda::msda_cast_f32_to_bf16_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
+        gv32, static_cast<__nv_bfloat16*>(grad_value), n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     MSDA_CUDA(cudaGetLastError());
   }
   return MSDA_OK;

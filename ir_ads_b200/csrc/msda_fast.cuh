@@ -250,6 +250,55 @@ __device__ __forceinline__ PointRec make_record(float x, float y, float aw, int 
   return r;
 }
 
+// ---- fused pre-op chain -----------------------------------------------------
+// FUSED kernels take what the module's two Linear layers produce -- raw sampling offsets
+// [B,Q,H,L,P,2] and attention logits [B,Q,H,L*P] -- plus the reference points [B,Q,L,2|4], and do the
+// softmax over L*P and the sampling-location affine (multi_scale_deform_attn.py:300-332) while they
+// build the records, so sampling_locations / attention_weights never exist in HBM.  The arithmetic
+// keeps torch's operation order (separate div / mul / add roundings, no fma), so the locations are
+// bit-identical to the unfused module's.
+struct FusedArgs {
+  const float* ref;   // reference_points [B, Q, L, ref_dim]
+  int ref_dim;        // 2: loc = ref + off / (W_l, H_l);  4: loc = ref_xy + off / P * ref_wh * 0.5
+  float inv_P;        // 1 / P
+};
+
+__device__ __forceinline__ float2 fused_location(const float2 off, const float* r, int ref_dim, int Hl, int Wl,
+                                                 float inv_P) {
+  float2 loc;
+  if (ref_dim == 2) {
+    loc.x = __fadd_rn(__ldg(r + 0), __fdiv_rn(off.x, (float)Wl));
+    loc.y = __fadd_rn(__ldg(r + 1), __fdiv_rn(off.y, (float)Hl));
+  } else {
+    loc.x = __fadd_rn(__ldg(r + 0), __fmul_rn(__fmul_rn(__fmul_rn(off.x, inv_P), __ldg(r + 2)), 0.5f));
+    loc.y = __fadd_rn(__ldg(r + 1), __fmul_rn(__fmul_rn(__fmul_rn(off.y, inv_P), __ldg(r + 3)), 0.5f));
+  }
+  return loc;
+}
+
+// softmax over the row's NP logits by the row's LANES lanes; e_i = exp(x_i - max) is left in
+// scratch[pt] (one float per point, any 4-byte stride) and the sum is returned: w_i = e_i / sum.
+template <int LANES, int STRIDE>
+__device__ __forceinline__ float row_softmax(const float* logits_row, float* scratch, int NP, int sub) {
+  float m = -3.402823466e38f;
+  for (int pt = sub; pt < NP; pt += LANES) {
+    const float x = __ldg(logits_row + pt);
+    scratch[pt * STRIDE] = x;
+    m = fmaxf(m, x);
+  }
+#pragma unroll
+  for (int k = LANES / 2; k > 0; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+  float sum = 0.0f;
+  for (int pt = sub; pt < NP; pt += LANES) {
+    const float e = expf(scratch[pt * STRIDE] - m);
+    scratch[pt * STRIDE] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int k = LANES / 2; k > 0; k >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, k);
+  return sum;
+}
+
 // =============================================================================================
 // Forward
 // =============================================================================================
@@ -257,18 +306,20 @@ __device__ __forceinline__ PointRec make_record(float x, float y, float aw, int 
 // TILED (persistent): software pipeline per warp -- wait for this item's raw loc/w in shared memory
 //   -> phase 1: records -> issue cp.async for the NEXT item's loc/w -> phase 2: gather (the long
 //   phase, hides the HBM latency of the copy).
-template <int D, typename VT, int PT, int THREADS, int ORDER>
+template <int D, typename VT, int PT, int THREADS, int ORDER, bool FUSED>
 #ifndef MSDA_FWD_MINB
 #define MSDA_FWD_MINB 6
 #endif
 __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_FWD_MINB : ((THREADS == 512) ? 3 : 1))
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                     const float* __restrict__ w, VT* __restrict__ out, int B, int S, int H, int L, int Q,
-                     int P, int64_t rows) {
+                     const float* __restrict__ w, VT* __restrict__ out, const FusedArgs fused, int B, int S, int H,
+                     int L, int Q, int P, int64_t rows) {
+  // FUSED: `loc` holds raw sampling offsets and `w` attention logits (see FusedArgs)
   using G = Geom<D, THREADS>;
   constexpr int LANES = G::LANES;
   constexpr bool STAGED = (ORDER == 1);
+  static_assert(!(FUSED && STAGED), "the fused pre-op chain is built for the single-pass row orders");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
@@ -300,16 +351,28 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       __syncwarp();
     }
     // ---- phase 1: records ----
-    if (cur.live) {
+    {
       const float2* lp = reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2);
       const float* wp = w + cur.row * (int64_t)NP;
-      for (int pt = sub; pt < NP; pt += LANES) {
-        const float2 xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
-        const float aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
-        const int l = level_of<PT>(pt, P);
-        const PointRec r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
-        s_cw[pt] = r.cw;
-        s_oc[pt] = r.oc;
+      float sm_sum = 1.0f;
+      // the softmax shuffles need the whole warp; dead rows read row 0 and simply produce nothing
+      if constexpr (FUSED) sm_sum = row_softmax<LANES, 1>(wp, reinterpret_cast<float*>(s_oc), NP, sub);
+      if (cur.live) {
+        const float* rp = FUSED ? fused.ref + (cur.row / H) * (int64_t)L * fused.ref_dim : nullptr;
+        for (int pt = sub; pt < NP; pt += LANES) {
+          float2 xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
+          float aw;
+          const int l = level_of<PT>(pt, P);
+          if constexpr (FUSED) {
+            aw = __fdiv_rn(__int_as_float(s_oc[pt]), sm_sum);
+            xy = fused_location(xy, rp + l * fused.ref_dim, fused.ref_dim, tab->H[l], tab->W[l], fused.inv_P);
+          } else {
+            aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
+          }
+          const PointRec r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+          s_cw[pt] = r.cw;
+          s_oc[pt] = r.oc;
+        }
       }
     }
     __syncwarp();
@@ -429,17 +492,19 @@ __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
 #ifndef MSDA_BWD_MINB
 #define MSDA_BWD_MINB 1
 #endif
-template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC>
+template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC, bool FUSED>
 __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_BWD_MINB : 1)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ w,
                      ACC* __restrict__ grad_value, float* __restrict__ grad_loc,
-                     float* __restrict__ grad_w, const DetScale* __restrict__ det, int B, int S, int H, int L,
-                     int Q, int P, int64_t rows) {
+                     float* __restrict__ grad_w, const DetScale* __restrict__ det, const FusedArgs fused, int B,
+                     int S, int H, int L, int Q, int P, int64_t rows) {
+  // FUSED: loc = raw offsets, w = logits in; grad_loc = grad of the offsets, grad_w = grad of the logits out
   using G = Geom<D, THREADS>;
   constexpr int LANES = G::LANES;
   constexpr bool STAGED = (ORDER == 1);
+  static_assert(!(FUSED && STAGED), "the fused pre-op chain is built for the single-pass row orders");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
@@ -475,16 +540,25 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
       cp_async_wait_all();
       __syncwarp();
     }
+    const float* rp = FUSED ? fused.ref + (cur.row / H) * (int64_t)L * fused.ref_dim : nullptr;
     {
       const float2* lp = reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2);
       const float* wp = w + cur.row * (int64_t)NP;
+      float sm_sum = 1.0f;
+      if constexpr (FUSED) sm_sum = row_softmax<LANES, 4>(wp, reinterpret_cast<float*>(s_fin) + 3, NP, sub);
       for (int pt = sub; pt < NP; pt += LANES) {
         float4 cw = zero;
         int4 fin = make_int4(0, __float_as_int(-1.0f), 0, 0);
         if (cur.live) {
-          const float2 xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
-          const float aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
+          float2 xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
+          float aw;
           const int l = level_of<PT>(pt, P);
+          if constexpr (FUSED) {
+            aw = __fdiv_rn(__int_as_float(s_fin[pt].w), sm_sum);
+            xy = fused_location(xy, rp + l * fused.ref_dim, fused.ref_dim, tab->H[l], tab->W[l], fused.inv_P);
+          } else {
+            aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
+          }
           const PointRec r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
           cw = r.cw;
           fin = make_int4(r.oc, __float_as_int(r.lw), __float_as_int(r.lh), __float_as_int(aw));
@@ -510,6 +584,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     float* glp = grad_loc + cur.row * (int64_t)NP * 2;
     float* gwp = grad_w + cur.row * (int64_t)NP;
 
+    float sm_dot = 0.0f;   // FUSED: sum_j grad_aw_j * aw_j of the row (softmax backward)
     for (int c0 = 0; c0 < NP; c0 += 4) {
       float d[16];
 #pragma unroll
@@ -564,8 +639,35 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           g_x = (hh * (d1 - d0) + lh * (d3 - d2)) * aw * (float)tab->W[l];
           g_y = (hw * (d2 - d0) + lw * (d3 - d1)) * aw * (float)tab->H[l];
         }
-        gwp[mine] = g_aw;
-        *reinterpret_cast<float2*>(glp + 2 * mine) = make_float2(g_x, g_y);
+        if constexpr (FUSED) {
+          // chain rule through loc = ref + off / (W,H)   or   ref_xy + off / P * ref_wh * 0.5
+          const int l = level_of<PT>(mine, P);
+          float2 g_off;
+          if (fused.ref_dim == 2) {
+            g_off = make_float2(__fdiv_rn(g_x, (float)tab->W[l]), __fdiv_rn(g_y, (float)tab->H[l]));
+          } else {
+            const float* r4 = rp + l * 4;
+            g_off = make_float2(g_x * 0.5f * __ldg(r4 + 2) * fused.inv_P, g_y * 0.5f * __ldg(r4 + 3) * fused.inv_P);
+          }
+          *reinterpret_cast<float2*>(glp + 2 * mine) = g_off;
+          s_fin[mine].y = __float_as_int(g_aw);   // this point's record is finished: park grad_aw there
+          sm_dot = fmaf(g_aw, aw, sm_dot);
+        } else {
+          gwp[mine] = g_aw;
+          *reinterpret_cast<float2*>(glp + 2 * mine) = make_float2(g_x, g_y);
+        }
+      }
+    }
+    if constexpr (FUSED) {
+      // softmax backward: grad_logit_i = aw_i * (grad_aw_i - sum_j grad_aw_j aw_j)
+#pragma unroll
+      for (int k = LANES / 2; k > 0; k >>= 1) sm_dot += __shfl_xor_sync(0xffffffffu, sm_dot, k);
+      __syncwarp();
+      if (cur.live) {
+        for (int pt = sub; pt < NP; pt += LANES) {
+          const int4 r = s_fin[pt];
+          gwp[pt] = __int_as_float(r.w) * (__int_as_float(r.y) - sm_dot);
+        }
       }
     }
     if (!has_next) break;

@@ -151,6 +151,90 @@ class MultiScaleDeformableAttnFunction(Function):
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
 
 
+# ------------------------------------------------------------------------------------------------
+# fused module path: softmax + sampling-location arithmetic inside the kernels
+# ------------------------------------------------------------------------------------------------
+def fused_supported(value: torch.Tensor, num_levels: int, num_points: int) -> bool:
+    """True when the fused kernels cover this problem (fast-kernel shapes, float32 / bfloat16 value,
+    non-deterministic mode); otherwise the module composes the pre-op chain in PyTorch."""
+    if not value.is_cuda or value.dtype not in (torch.float32, torch.bfloat16) or value.dim() != 4:
+        return False
+    _, S, H, D = value.shape
+    return bool(_lib.lib().msda_fused_supported(D, num_levels, num_points, S, H, _DTYPE_TAG[value.dtype],
+                                                _flags(True)))
+
+
+class MSDeformAttnFusedFunction(Function):
+    """``apply(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points)``
+    -> ``[B, Q, H*D]``.  ``sampling_offsets [B,Q,H,L,P,2]`` and ``attn_logits [B,Q,H,L*P]`` are the raw
+    outputs of the module's two Linear layers (float32); ``reference_points [B,Q,L,2|4]`` float32.
+    Equivalent to softmax + location affine (multi_scale_deform_attn.py:300-332) followed by
+    MultiScaleDeformableAttnFunction, without materialising locations / weights or their gradients."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points):
+        B, S, H, D = value.shape
+        _, Q, _, L, P, _ = sampling_offsets.shape
+        for name, t in (("value", value), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
+                        ("reference_points", reference_points), ("spatial_shapes", spatial_shapes),
+                        ("level_start_index", level_start_index)):
+            _require(t.is_cuda and t.device == value.device, f"{name} must be a CUDA tensor on {value.device}")
+            _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+        _require(sampling_offsets.dtype == torch.float32 and attn_logits.dtype == torch.float32
+                 and reference_points.dtype == torch.float32, "offsets / logits / reference_points must be float32")
+        _require(tuple(attn_logits.shape) == (B, Q, H, L * P), "attn_logits must be [B, Q, H, L*P]")
+        ref_dim = reference_points.shape[-1]
+        _require(tuple(reference_points.shape) == (B, Q, L, ref_dim) and ref_dim in (2, 4),
+                 "reference_points must be [B, Q, L, 2 or 4]")
+        out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
+        stream = torch.cuda.current_stream(value.device).cuda_stream
+        status = _lib.lib().msda_fused_forward(
+            ctypes.c_void_p(stream), _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_offsets),
+            _ptr(attn_logits), _ptr(reference_points), ref_dim, B, S, H, D, L, Q, P, _ptr(out),
+            _DTYPE_TAG[value.dtype], _flags(False))
+        _lib.check(status, "msda_fused_forward")
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points = ctx.saved_tensors
+        B, S, H, D = value.shape
+        _, Q, _, L, P, _ = sampling_offsets.shape
+        ref_dim = reference_points.shape[-1]
+        grad_output = grad_output.contiguous()
+        grad_value = torch.empty_like(value)
+        grad_off = torch.empty_like(sampling_offsets)
+        grad_logits = torch.empty_like(attn_logits)
+        flags = _flags(True) & ~_lib.FLAG_DETERMINISTIC
+        tag = _DTYPE_TAG[value.dtype]
+        handle = _lib.lib()
+        ws_bytes = int(handle.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, tag, flags))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
+        stream = torch.cuda.current_stream(value.device).cuda_stream
+        status = handle.msda_fused_backward(
+            ctypes.c_void_p(stream), _ptr(grad_output), _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
+            _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points), ref_dim, B, S, H, D, L, Q, P,
+            _ptr(grad_value), _ptr(grad_off), _ptr(grad_logits), _ptr(ws) if ws is not None else ctypes.c_void_p(0),
+            ws_bytes, tag, flags)
+        _lib.check(status, "msda_fused_backward")
+        grad_ref = None
+        if ctx.needs_input_grad[5]:
+            # d loc / d ref: identity on (x, y); for boxes additionally off / P * 0.5 on (w, h).  Rare path
+            # (DINO detaches its reference points), so it is composed from grad_offsets in PyTorch.
+            wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(grad_off.dtype)   # (W_l, H_l)
+            if ref_dim == 2:
+                grad_ref = (grad_off * wh[None, None, None, :, None, :]).sum(dim=(2, 4))
+            else:
+                scale = reference_points[:, :, None, :, None, 2:] * (0.5 / P)          # d loc / d off
+                g_loc = torch.where(scale != 0, grad_off / scale, torch.zeros_like(grad_off))
+                g_xy = g_loc.sum(dim=(2, 4))
+                g_wh = (g_loc * sampling_offsets * (0.5 / P)).sum(dim=(2, 4))
+                grad_ref = torch.cat([g_xy, g_wh], -1)
+        return grad_value, None, None, grad_off, grad_logits, grad_ref
+
+
 def debug_bookkeeping(sampling_loc: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,
                       spatial_size: int, channels: int):
     """Integer bookkeeping of the float kernels (test hook, see include/msda.h)."""

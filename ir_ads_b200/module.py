@@ -24,7 +24,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from .functional import MultiScaleDeformableAttnFunction
+from .functional import MSDeformAttnFusedFunction, MultiScaleDeformableAttnFunction, fused_supported
 
 
 def _is_power_of_2(n: int) -> bool:
@@ -62,6 +62,9 @@ class MultiScaleDeformableAttention(nn.Module):
         self.value_proj = nn.Linear(embed_dim, embed_dim)
         self.output_proj = nn.Linear(embed_dim, embed_dim)
         self._shape_checks = {}
+        # fused pre-op chain (softmax + sampling-location arithmetic inside the kernels); set False to
+        # run the reference's step-by-step composition around the core op instead
+        self.fuse_pre_ops = True
         self.init_weights()
 
     def init_weights(self) -> None:
@@ -117,8 +120,30 @@ class MultiScaleDeformableAttention(nn.Module):
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], float(0))
         value = value.view(bs, num_value, H, -1)
+        if not value.is_cuda:
+            raise RuntimeError("MultiScaleDeformableAttention: Not implemented on the CPU "
+                               "(the B200 build has no PyTorch fallback)")
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError(
+                f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
         offsets = self.sampling_offsets(query).view(bs, num_query, H, L, P, 2)
-        weights = self.attention_weights(query).view(bs, num_query, H, L * P).softmax(-1).view(bs, num_query, H, L, P)
+        logits = self.attention_weights(query).view(bs, num_query, H, L * P)
+
+        io_dtype = value.dtype
+        if io_dtype == torch.float16:
+            value = value.float()
+        if self.fuse_pre_ops and fused_supported(value, L, P):
+            output = MSDeformAttnFusedFunction.apply(
+                value.contiguous(), spatial_shapes, level_start_index, offsets.float().contiguous(),
+                logits.float().contiguous(), reference_points.float().contiguous())
+            if output.dtype != io_dtype:
+                output = output.to(io_dtype)
+            output = self.output_proj(output)
+            if not self.batch_first:
+                output = output.permute(1, 0, 2)
+            return self.dropout(output) + identity
+
+        weights = logits.softmax(-1).view(bs, num_query, H, L, P)
 
         if reference_points.shape[-1] == 2:
             normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
@@ -130,12 +155,6 @@ class MultiScaleDeformableAttention(nn.Module):
             raise ValueError(
                 f"Last dim of reference_points must be 2 or 4, but get {reference_points.shape[-1]} instead.")
 
-        if not value.is_cuda:
-            raise RuntimeError("MultiScaleDeformableAttention: Not implemented on the CPU "
-                               "(the B200 build has no PyTorch fallback)")
-        io_dtype = value.dtype
-        if io_dtype == torch.float16:
-            value = value.float()
         aux = torch.float64 if value.dtype == torch.float64 else torch.float32
         output = MultiScaleDeformableAttnFunction.apply(
             value.contiguous(), spatial_shapes, level_start_index, locations.to(aux).contiguous(),

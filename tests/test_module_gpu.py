@@ -111,3 +111,93 @@ def test_module_rejects_wrong_value_length():
     q = torch.randn(1, 19, 64, device=DEV)                      # 19 != 20
     with pytest.raises(AssertionError):
         m(q, reference_points=torch.rand(1, 19, 2, 2, device=DEV), spatial_shapes=shapes, level_start_index=lsi)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused pre-op chain (softmax + sampling-location arithmetic inside the kernels)
+# ------------------------------------------------------------------------------------------------
+def _compose_unfused(value, shapes, lsi, offsets, logits, ref, P):
+    """py:300-332 in PyTorch, then the unfused op."""
+    from ir_ads_b200 import MultiScaleDeformableAttnFunction
+    B, Q, H, L, _, _ = offsets.shape
+    w = logits.softmax(-1).view(B, Q, H, L, P)
+    if ref.shape[-1] == 2:
+        norm = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+        loc = ref[:, :, None, :, None, :] + offsets / norm[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + offsets / P * ref[:, :, None, :, None, 2:] * 0.5
+    return MultiScaleDeformableAttnFunction.apply(value, shapes, lsi, loc.contiguous(), w.contiguous(), 64)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ref_dim,D,L,P", [(2, 32, 4, 4), (4, 32, 4, 4), (2, 64, 3, 8), (4, 16, 2, 3), (2, 128, 1, 5)])
+def test_fused_function_matches_composition(ref_dim, D, L, P, dtype):
+    from ir_ads_b200.functional import MSDeformAttnFusedFunction, fused_supported
+    from ir_ads_b200.workloads import level_tensors
+
+    torch.manual_seed(7)
+    levels = [(11, 17), (6, 9), (3, 5), (2, 3)][:L]
+    shapes, lsi = level_tensors(levels, DEV)
+    S = sum(h * w for h, w in levels)
+    B, Q, H = 2, 53, 4
+    value = torch.randn(B, S, H, D, device=DEV).to(dtype)
+    assert fused_supported(value, L, P)
+    offsets = torch.randn(B, Q, H, L, P, 2, device=DEV) * 3.0
+    logits = torch.randn(B, Q, H, L * P, device=DEV) * 2.0
+    ref = torch.rand(B, Q, L, ref_dim, device=DEV) * 1.2 - 0.1          # some samples fall outside the map
+    if ref_dim == 4:
+        ref[..., 2:] = ref[..., 2:].abs() * 0.4 + 0.05
+    go = torch.randn(B, Q, H * D, device=DEV).to(dtype)
+
+    leaves_a = [t.clone().requires_grad_(True) for t in (value, offsets, logits, ref)]
+    out_a = MSDeformAttnFusedFunction.apply(leaves_a[0], shapes, lsi, leaves_a[1], leaves_a[2], leaves_a[3])
+    out_a.backward(go)
+    leaves_b = [t.clone().requires_grad_(True) for t in (value, offsets, logits, ref)]
+    out_b = _compose_unfused(leaves_b[0], shapes, lsi, leaves_b[1], leaves_b[2], leaves_b[3], P)
+    out_b.backward(go)
+
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+
+    def close(a, b, what, t=tol):
+        a, b = a.double(), b.double()
+        assert (a - b).abs().max() <= t * b.abs().max() + 1e-6, (what, float((a - b).abs().max()), float(b.abs().max()))
+
+    close(out_a, out_b, "out")
+    close(leaves_a[0].grad, leaves_b[0].grad, "grad_value")
+    # grad wrt offsets is discontinuous where a sample sits on a pixel boundary: same locations in both
+    # paths (bit-identical arithmetic), so no masking is needed here
+    close(leaves_a[1].grad, leaves_b[1].grad, "grad_offsets", 1e-4 if dtype == torch.float32 else tol)
+    close(leaves_a[2].grad, leaves_b[2].grad, "grad_logits", 1e-4 if dtype == torch.float32 else tol)
+    close(leaves_a[3].grad, leaves_b[3].grad, "grad_reference_points", 1e-4 if dtype == torch.float32 else tol)
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_module_fused_and_unfused_paths_agree(ref_dim):
+    from ir_ads_b200 import MultiScaleDeformableAttention
+    from ir_ads_b200.workloads import level_tensors
+
+    torch.manual_seed(3)
+    levels = [(12, 17), (6, 9), (3, 5), (2, 3)]
+    shapes, lsi = level_tensors(levels, DEV)
+    S = sum(h * w for h, w in levels)
+    B, Q = 2, (S if ref_dim == 2 else 31)
+    m = MultiScaleDeformableAttention(dropout=0.0, batch_first=True).to(DEV)
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.05)
+        m.attention_weights.weight.normal_(0, 0.2)
+    q = torch.randn(B, Q, 256, device=DEV)
+    val = None if ref_dim == 2 else torch.randn(B, S, 256, device=DEV)
+    ref_pts = torch.rand(B, Q, 4, ref_dim, device=DEV)
+    mask = torch.zeros(B, S, dtype=torch.bool, device=DEV)
+    mask[0, :5] = True
+    res = {}
+    for fused in (True, False):
+        m.fuse_pre_ops = fused
+        m.zero_grad(set_to_none=True)
+        qq = q.clone().requires_grad_(True)
+        out = m(qq, value=val, key_padding_mask=mask, reference_points=ref_pts, spatial_shapes=shapes,
+                level_start_index=lsi)
+        out.square().mean().backward()
+        res[fused] = [out.detach(), qq.grad] + [p.grad.clone() for p in m.parameters()]
+    for a, b in zip(res[True], res[False]):
+        assert (a - b).abs().max() <= 2e-5 * b.abs().max() + 1e-7, float((a - b).abs().max() / b.abs().max())
