@@ -343,6 +343,7 @@ def main():
             "data": "synthetic", "config": config_dict(wl, args),
             "roofline": {"bound": "hbm", "kernel": bwd_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
                 "traffic": ncu_traffic(wl.name, bwd_name) if args.flags == 0 else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
                 "launch_ms": bwd_ms, "note": "launch_ms includes the grad_value zero-fill memset issued by msda_backward",

@@ -201,3 +201,51 @@ def test_module_fused_and_unfused_paths_agree(ref_dim):
         res[fused] = [out.detach(), qq.grad] + [p.grad.clone() for p in m.parameters()]
     for a, b in zip(res[True], res[False]):
         assert (a - b).abs().max() <= 2e-5 * b.abs().max() + 1e-7, float((a - b).abs().max() / b.abs().max())
+
+
+def test_six_layer_stack_is_cuda_graph_capturable():
+    """SURVEY 8f-2 (host side): no per-call device->host sync and no library-side allocation, so a
+    6-layer encoder-style stack of module forward+backward replays from ONE CUDA graph."""
+    from ir_ads_b200 import MultiScaleDeformableAttention
+    from ir_ads_b200.workloads import level_tensors
+
+    torch.manual_seed(1)
+    levels = [(12, 17), (6, 9), (3, 5), (2, 3)]
+    shapes, lsi = level_tensors(levels, DEV)
+    S = sum(h * w for h, w in levels)
+    layers = torch.nn.ModuleList([MultiScaleDeformableAttention(dropout=0.0, batch_first=True) for _ in range(6)]).to(DEV)
+    for m in layers:
+        with torch.no_grad():
+            m.sampling_offsets.weight.normal_(0, 0.05)
+            m.attention_weights.weight.normal_(0, 0.2)
+    x = torch.randn(2, S, 256, device=DEV, requires_grad=True)
+    ref_pts = torch.rand(2, S, 4, 2, device=DEV)
+
+    def step():
+        h = x
+        for m in layers:
+            h = m(h, reference_points=ref_pts, spatial_shapes=shapes, level_start_index=lsi)
+        h.square().mean().backward()
+        return h
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                       # warm-up: shape check cached, allocator primed
+        for _ in range(3):
+            layers.zero_grad(set_to_none=True); x.grad = None
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    layers.zero_grad(set_to_none=True); x.grad = None
+    eager = step().detach().clone()
+    eager_grad = x.grad.detach().clone()
+    layers.zero_grad(set_to_none=True); x.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        captured = step()
+    x.grad.zero_()
+    for p in layers.parameters():
+        p.grad.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(captured, eager)
+    assert torch.allclose(x.grad, eager_grad, rtol=1e-4, atol=1e-7)     # grad_value atomics reorder
