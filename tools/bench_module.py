@@ -79,6 +79,50 @@ def run(kind, batch, iters, mode, dev="cuda:0", amp=None):
             "gpts_s": round(pts / t / 1e6, 3)}
 
 
+def run_stack(batch, iters, graph, amp=None, dev="cuda:0"):
+    """6-layer DeformableEncoder (MSDA + LayerNorm + FFN per layer) forward+backward at the DINO-R50 shape."""
+    from ir_ads_b200 import encoder
+    levels = LEVELS["dino_r50"]
+    shapes, lsi = level_tensors(levels, dev)
+    S = sum(h * w for h, w in levels)
+    torch.manual_seed(0)
+    enc = encoder.DeformableEncoder(attn_dropout=0.0, ffn_dropout=0.0).to(dev)
+    x = torch.randn(batch, S, 256, device=dev, requires_grad=True)
+    pos = torch.randn(batch, S, 256, device=dev)
+    ref = encoder.get_reference_points(levels, torch.ones(batch, 4, 2, device=dev), dev)
+    go = torch.randn(batch, S, 256, device=dev)
+
+    def step():
+        with torch.autocast("cuda", dtype=amp, enabled=amp is not None):
+            out = enc(x, query_pos=pos, reference_points=ref, spatial_shapes=shapes, level_start_index=lsi)
+        out.backward(go.to(out.dtype))
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    runner = step
+    if graph:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        runner = g.replay
+    times = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        runner()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    t = statistics.median(times)
+    pts = 6 * batch * S * 8 * 4 * 4
+    return {"kind": "encoder_stack_6_layers", "batch": batch, "mode": "cuda_graph" if graph else "eager",
+            "amp": str(amp), "ms": round(t, 3), "gpts_s": round(pts / t / 1e6, 3)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
@@ -96,6 +140,12 @@ def main():
             r = run(kind, a.batch, a.iters, mode, amp=torch.bfloat16)
             rows.append(r)
             print(json.dumps(r), flush=True)
+    for b in sorted({a.batch, 1}):
+        for graph in (False, True):
+            for amp in (None, torch.bfloat16):
+                r = run_stack(b, a.iters, graph, amp)
+                rows.append(r)
+                print(json.dumps(r), flush=True)
     if a.out:
         with open(a.out, "w") as f:
             json.dump(rows, f, indent=1)
