@@ -116,10 +116,30 @@ class ClockSampler:
                 pass
             self._stop.wait(0.02)
 
+    def _smi_loop(self):
+        """Fallback when NVML's python binding is missing: poll nvidia-smi (B200_PROFILING.md's clocks line)."""
+        import subprocess
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(int(f[0]))
+                self.max_mhz = int(f[1])
+                for name, val in zip(names, f[2:]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
     def start(self):
-        if self._nvml is not None:
-            self._thread = threading.Thread(target=self._loop, daemon=True)
-            self._thread.start()
+        target = self._loop if self._nvml is not None else self._smi_loop
+        self._thread = threading.Thread(target=target, daemon=True)
+        self._thread.start()
 
     def stop(self):
         self._stop.set()
