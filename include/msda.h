@@ -80,6 +80,8 @@ extern "C" {
 #define MSDA_FLAG_ORDER_TILED (1u << 3)
 /* One CTA = a strip of consecutive queries of ONE head (any Q): x-adjacent queries re-use corner lines in L1. */
 #define MSDA_FLAG_ORDER_STRIP (1u << 4)
+/* Encoder form only (Q == S): one CTA = an 8x4-pixel tile (at D=32) of one level and ONE head, non-persistent. */
+#define MSDA_FLAG_ORDER_TILE2D (1u << 5)
 
 int msda_abi_version(void);
 

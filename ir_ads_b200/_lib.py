@@ -23,6 +23,7 @@ FLAG_FORCE_GENERIC = 1 << 1
 FLAG_ORDER_LINEAR = 1 << 2
 FLAG_ORDER_TILED = 1 << 3
 FLAG_ORDER_STRIP = 1 << 4
+FLAG_ORDER_TILE2D = 1 << 5
 ABI_VERSION = 1
 
 _lock = threading.Lock()

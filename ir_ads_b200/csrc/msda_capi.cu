@@ -129,8 +129,15 @@ bool use_tiled(const Dims& d, unsigned flags) {
 }
 bool use_strip(const Dims& d, unsigned flags) {
   (void)d;
-  return (flags & MSDA_FLAG_ORDER_STRIP) && !(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED));
+  return (flags & MSDA_FLAG_ORDER_STRIP) && !(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED | MSDA_FLAG_ORDER_TILE2D));
 }
+bool use_tile2d(const Dims& d, unsigned flags) {
+  return d.Q == d.S && (flags & MSDA_FLAG_ORDER_TILE2D) && !(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED));
+}
+// TILE2D launches an upper bound on the tile count that needs only S and L (the level shapes stay on the
+// device): sum_l ceil(H_l/TH)*ceil(W_l/TW) is ~1.03 * S/RPC for image pyramids; 25 % + 32 tiles per level of
+// slack covers them, the kernel's grid-stride step covers anything else.
+int64_t tile2d_bound(const Dims& d, int rpc) { return ((int64_t)d.S + rpc - 1) / rpc * 5 / 4 + 32 * (int64_t)d.L; }
 // experiment knob (bits 16-17): CTA size of the TILED kernels; 0 = default
 int tiled_threads(unsigned flags) { return ((flags >> 16) & 3u) == 1u ? 512 : 1024; }
 
@@ -146,6 +153,7 @@ int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
   if (TILED == 1) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
   if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
+  if (TILED == 3) grid = (unsigned)((int64_t)d.B * d.H * tile2d_bound(d, G::RPC));
   k<<<grid, THREADS, smem, st>>>((const VT*)value, shapes, lsi, (const float*)loc, (const float*)w, (VT*)out, fa,
                                  d.B, d.S, d.H, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -166,6 +174,7 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
   if (TILED == 1) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
   if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
+  if (TILED == 3) grid = (unsigned)((int64_t)d.B * d.H * tile2d_bound(d, G::RPC));
   k<<<grid, THREADS, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
                                  gv, (float*)gl, (float*)gw, det, fa, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -175,6 +184,7 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
 
 #define MSDA_DISPATCH_ORDER(D_, VT_, PT_, CALL)                                      \
   do {                                                                               \
+    if (use_tile2d(d, flags)) return CALL(D_, VT_, PT_, 256, 3);                     \
     if (use_strip(d, flags)) return CALL(D_, VT_, PT_, 256, 2);                      \
     if (!use_tiled(d, flags)) return CALL(D_, VT_, PT_, 256, 0);                     \
     if (tiled_threads(flags) == 512) return CALL(D_, VT_, PT_, 512, 1);              \
@@ -212,7 +222,7 @@ int bwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const vo
              void* gw) {
   // default row order of the backward: STRIP (measured 3 % faster than LINEAR at cfg 2: fewer L1 misses
   // on the crossbar-bound kernel); the forward keeps LINEAR
-  if (!(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED))) flags |= MSDA_FLAG_ORDER_STRIP;
+  if (!(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED | MSDA_FLAG_ORDER_TILE2D))) flags |= MSDA_FLAG_ORDER_STRIP;
 #define CALL_BWD(D_, VT_, PT_, TH_, TL_) \
   launch_bwd_fast<D_, VT_, PT_, TH_, TL_, float>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw, nullptr)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);

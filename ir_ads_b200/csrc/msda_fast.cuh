@@ -160,22 +160,26 @@ __device__ __forceinline__ void stage_row(float2* raw_xy, float* raw_w, const fl
 // Row iterator: yields this thread's row for every work item of the CTA.
 // ORDER: 0 = LINEAR, 1 = TILED (persistent grid-stride), 2 = STRIP (one CTA = RPC consecutive queries
 // of ONE head; x-adjacent queries of a head share bilinear corners, so the CTA re-uses lines in L1 --
-// needs no knowledge of the level shapes and works for any Q).
+// needs no knowledge of the level shapes and works for any Q), 3 = TILE2D (encoder form, Q == S: one CTA =
+// a TW x TH pixel tile of one level and ONE head, tile index slowest; the grid is an upper bound computed
+// from S alone -- surplus CTAs exit, a grid-stride step covers pathological pyramids -- so the level shapes
+// never have to be known on the host).
 template <int D, int THREADS, int ORDER>
 struct RowWalk {
   using G = Geom<D, THREADS>;
   int64_t item, n_items, rows;
-  int rin;
+  int rin, BH;
   __device__ __forceinline__ RowWalk(const LevelTab* tab, int B, int H, int64_t rows_) : rows(rows_) {
     rin = threadIdx.x / G::LANES;
     item = blockIdx.x;
-    if (ORDER == 1) n_items = (int64_t)B * H * tab->total_tiles;
+    BH = B * H;
+    if (ORDER == 1 || ORDER == 3) n_items = (int64_t)B * H * tab->total_tiles;
     else if (ORDER == 2) n_items = (int64_t)B * H * ((rows / ((int64_t)B * H) + G::RPC - 1) / G::RPC);
     else n_items = (rows + G::RPC - 1) / G::RPC;
   }
   __device__ __forceinline__ bool done() const { return item >= n_items; }
   // LINEAR / STRIP kernels are launched with one CTA per item: a single pass, no loop-carried state.
-  __device__ __forceinline__ void next() { item = (ORDER == 1) ? item + gridDim.x : n_items; }
+  __device__ __forceinline__ void next() { item = (ORDER == 1 || ORDER == 3) ? item + gridDim.x : n_items; }
   __device__ __forceinline__ RowRef get(const LevelTab* tab, int L, int H, int Q) const {
     RowRef r;
     if (ORDER == 2) {
@@ -188,6 +192,24 @@ struct RowWalk {
       r.b = b;
       r.h = h;
       r.row = r.live ? ((int64_t)b * Q + q) * H + h : 0;
+    } else if (ORDER == 3) {
+      const unsigned it = (unsigned)item;
+      const unsigned t = it / (unsigned)BH, r = it - t * (unsigned)BH;
+      const int b = (int)(r / (unsigned)H), h = (int)(r - (unsigned)b * (unsigned)H);
+      int l = 0;
+#pragma unroll 1
+      for (int k = 1; k < L; ++k)
+        if ((int)t >= tab->tile_begin[k]) l = k;
+      const int tt = (int)t - tab->tile_begin[l];
+      const int ty = tt / tab->tiles_x[l], tx = tt - ty * tab->tiles_x[l];
+      const int y = ty * G::TH + rin / G::TW, x = tx * G::TW + rin % G::TW;
+      const int q = tab->start[l] + y * tab->W[l] + x;
+      RowRef rr;
+      rr.live = (y < tab->H[l]) && (x < tab->W[l]) && (q < Q);
+      rr.b = b;
+      rr.h = h;
+      rr.row = rr.live ? ((int64_t)b * Q + q) * H + h : 0;
+      return rr;
     } else if (ORDER == 1) {
       const int h = (int)(item % H);
       const int64_t bt = item / H;
@@ -342,11 +364,12 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   RowRef cur = walk.get(tab, L, H, Q);
   if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
   while (true) {
-    walk.next();
-    const bool has_next = !walk.done();
+    bool has_next = false;
     RowRef nxt = cur;
-    if (has_next) nxt = walk.get(tab, L, H, Q);
-    if (STAGED) {
+    if constexpr (STAGED) {   // software pipeline: the next item is known (and its loc/w requested) early
+      walk.next();
+      has_next = !walk.done();
+      if (has_next) nxt = walk.get(tab, L, H, Q);
       cp_async_wait_all();
       __syncwarp();
     }
@@ -406,9 +429,16 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       }
       st4(out + cur.row * D + sub * 4, acc);
     }
-    if (!has_next) break;
-    __syncwarp();   // records are rewritten by the next work item
-    cur = nxt;
+    if constexpr (STAGED) {
+      if (!has_next) break;
+      __syncwarp();   // records are rewritten by the next work item
+      cur = nxt;
+    } else {
+      walk.next();    // single-pass orders end here; TILE2D only continues for a pathological pyramid
+      if (walk.done()) break;
+      __syncwarp();
+      cur = walk.get(tab, L, H, Q);
+    }
   }
 }
 
@@ -490,7 +520,7 @@ __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
 }
 
 #ifndef MSDA_BWD_MINB
-#define MSDA_BWD_MINB 1
+#define MSDA_BWD_MINB 4
 #endif
 template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC, bool FUSED>
 __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_BWD_MINB : 1)
@@ -530,15 +560,19 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   if (walk.done()) return;
   RowRef cur = walk.get(tab, L, H, Q);
   if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
-  float4 go = cur.live ? ld4(grad_out + cur.row * D + sub * 4) : zero;
+  float4 go = zero;
+  if (STAGED && cur.live) go = ld4(grad_out + cur.row * D + sub * 4);
   while (true) {
-    walk.next();
-    const bool has_next = !walk.done();
+    bool has_next = false;
     RowRef nxt = cur;
-    if (has_next) nxt = walk.get(tab, L, H, Q);
-    if (STAGED) {
+    if constexpr (STAGED) {
+      walk.next();
+      has_next = !walk.done();
+      if (has_next) nxt = walk.get(tab, L, H, Q);
       cp_async_wait_all();
       __syncwarp();
+    } else {
+      go = cur.live ? ld4(grad_out + cur.row * D + sub * 4) : zero;
     }
     const float* rp = FUSED ? fused.ref + (cur.row / H) * (int64_t)L * fused.ref_dim : nullptr;
     {
@@ -569,9 +603,11 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     }
     __syncwarp();
     float4 go_next = zero;
-    if (has_next) {
-      if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
-      if (nxt.live) go_next = ld4(grad_out + nxt.row * D + sub * 4);
+    if constexpr (STAGED) {
+      if (has_next) {
+        stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
+        if (nxt.live) go_next = ld4(grad_out + nxt.row * D + sub * 4);
+      }
     }
 
     constexpr bool DET = sizeof(ACC) == 8;
@@ -598,14 +634,21 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           const int o01 = o00 + ((oc & 1) ? HD : 0);
           const int dy = (oc & 2) ? tab->W[l] * HD : 0;
           const int o10 = o00 + dy, o11 = o01 + dy;
+#ifdef MSDA_EXP_NO_GATHER   // experiment builds only (tools/ablate.sh): what does the scatter cost alone?
+          const float4 v00 = cw, v01 = cw, v10 = cw, v11 = cw;
+#else
           const float4 v00 = ld4(vimg + o00);
           const float4 v01 = ld4(vimg + o01);
           const float4 v10 = ld4(vimg + o10);
           const float4 v11 = ld4(vimg + o11);
+#endif
           d[4 * j + 0] = dot4(go, v00);
           d[4 * j + 1] = dot4(go, v01);
           d[4 * j + 2] = dot4(go, v10);
           d[4 * j + 3] = dot4(go, v11);
+#ifdef MSDA_EXP_NO_RED      // experiment builds only: what does the gather cost alone?
+          if (cw.x == 12345.678f) scatter4(reinterpret_cast<float*>(gimg) + o00, cw.x, go_s, gscale);
+#else
           if constexpr (DET) {
             if (cw.x != 0.0f) scatter4_det<LANES>(gimg + o00, cw.x, go_s, gscale);
             if (cw.y != 0.0f) scatter4_det<LANES>(gimg + o01, cw.y, go_s, gscale);
@@ -617,6 +660,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             if (cw.z != 0.0f) scatter4(gimg + o10, cw.z, go_s, gscale);
             if (cw.w != 0.0f) scatter4(gimg + o11, cw.w, go_s, gscale);
           }
+#endif
         } else {
           d[4 * j + 0] = 0.f; d[4 * j + 1] = 0.f; d[4 * j + 2] = 0.f; d[4 * j + 3] = 0.f;
         }
@@ -670,10 +714,17 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         }
       }
     }
-    if (!has_next) break;
-    __syncwarp();   // records are rewritten by the next work item
-    cur = nxt;
-    go = go_next;
+    if constexpr (STAGED) {
+      if (!has_next) break;
+      __syncwarp();   // records are rewritten by the next work item
+      cur = nxt;
+      go = go_next;
+    } else {
+      walk.next();
+      if (walk.done()) break;
+      __syncwarp();
+      cur = walk.get(tab, L, H, Q);
+    }
   }
 }
 

@@ -163,15 +163,29 @@ def test_tiled_and_linear_row_orders_agree(D, P, threads_knob, dtype):
     go = torch.randn(2, value.shape[1], 4 * D, generator=torch.Generator().manual_seed(1)).to(dtype)
     tiled = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_ORDER_TILED | (threads_knob << 16))
     linear = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_ORDER_LINEAR)
-    strip = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_ORDER_STRIP)
-    assert np.array_equal(strip[0], linear[0]) and np.array_equal(strip[2], linear[2]) and np.array_equal(strip[3], linear[3])
-    assert_close(strip[1], linear[1], 1e-5 if dtype == torch.float32 else 1e-2, 1e-6, "grad_value (strip)")
+    for flag in (_lib.FLAG_ORDER_STRIP, _lib.FLAG_ORDER_TILE2D):
+        other = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=flag)
+        assert np.array_equal(other[0], linear[0]) and np.array_equal(other[2], linear[2]) and np.array_equal(other[3], linear[3])
+        assert_close(other[1], linear[1], 1e-5 if dtype == torch.float32 else 1e-2, 1e-6, f"grad_value (order flag {flag})")
     assert np.array_equal(tiled[0], linear[0])
     assert np.array_equal(tiled[2], linear[2]) and np.array_equal(tiled[3], linear[3])
     assert_close(tiled[1], linear[1], 1e-5 if dtype == torch.float32 else 1e-2, 1e-6, "grad_value")
     if dtype == torch.float32:
         ref = msda_c.forward(value.numpy(), shapes.numpy(), lsi.numpy(), loc.numpy(), w.numpy(), np.float64)
         assert_close(tiled[0], ref, 1e-5, 1e-6, "tiled out vs oracle")
+
+
+def test_tile2d_order_on_a_pathological_pyramid():
+    """1-pixel-wide levels make the tile count exceed the launch bound derived from S: the kernel's
+    grid-stride step must still cover every query."""
+    _, _lib, _, workloads, _, _ = _mods()
+    levels = [(300, 1), (1, 200), (64, 1), (1, 1)]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 1, 0, 2, 32, 4, "encoder", "model", 3)
+    go = torch.randn(1, value.shape[1], 64, generator=torch.Generator().manual_seed(1))
+    a = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_ORDER_TILE2D)
+    b = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_ORDER_LINEAR)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert_close(a[1], b[1], 1e-5, 1e-6, "grad_value")
 
 
 @pytest.mark.parametrize("dtype,D", [(torch.float32, 32), (torch.bfloat16, 32), (torch.float32, 30), (torch.float64, 32),
