@@ -134,6 +134,35 @@ int msda_fused_backward(void* stream, const void* grad_output, const void* value
                         size_t workspace_bytes, int dtype, unsigned flags);
 
 /*
+ * DCNv3 core op: the other native op of detrex._C, same gather/scatter core.
+ *   msda_dcnv3_forward   replaces dcnv3_im2col_cuda<T>
+ *       (/root/reference/detrex/layers/csrc/DCNv3/dcnv3_im2col_cuda.cuh:840-868), i.e. _C.dcnv3_forward
+ *       (csrc/vision.cpp:57); msda_dcnv3_backward replaces dcnv3_col2im_cuda<T> (:870-), _C.dcnv3_backward.
+ * Argument order follows those launchers.  Layouts (contiguous, channels last, as dcn_v3.py:464-489):
+ *   input  [N, H_in, W_in, group*group_channels]   dtype (MSDA_F32 or MSDA_BF16)
+ *   offset [N, H_out, W_out, group*K*2] float, K = kernel_h*kernel_w, point index = i*kernel_h + j
+ *          with i over kernel_w (the reference kernel's loop order), (x, y) per point, in pixels
+ *   mask   [N, H_out, W_out, group*K]   float
+ *   output / grad_output [N, H_out, W_out, group*group_channels] dtype
+ * The input is NOT padded by the caller: pad_h / pad_w only shift the sampling grid and samples outside
+ * the map read zeros, exactly like the reference kernel.  Supported: group_channels in {16,32,64,128},
+ * K <= 64, float32 / bfloat16 input (MSDA_ERR_UNSUPPORTED otherwise).  bfloat16 backward needs a
+ * workspace of N*H_in*W_in*C floats.
+ */
+int msda_dcnv3_forward(void* stream, const void* input, const float* offset, const float* mask,
+                       int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                       int dilation_h, int dilation_w, int group, int group_channels, float offset_scale,
+                       int batch, int height_in, int width_in, int height_out, int width_out,
+                       void* output, int dtype, unsigned flags);
+int msda_dcnv3_backward(void* stream, const void* grad_output, const void* input, const float* offset,
+                        const float* mask, int kernel_h, int kernel_w, int stride_h, int stride_w,
+                        int pad_h, int pad_w, int dilation_h, int dilation_w, int group,
+                        int group_channels, float offset_scale, int batch, int height_in, int width_in,
+                        int height_out, int width_out, void* grad_input, float* grad_offset,
+                        float* grad_mask, void* workspace, size_t workspace_bytes, int dtype,
+                        unsigned flags);
+
+/*
  * Test hook: the integer bookkeeping the float kernels derive from every sampling point.
  *   corner_offsets [B*Q*H*L*P, 4] int64  flat element offset (channel 0) of the four bilinear
  *                  corners inside `value`, -1 for a zero-padded corner or a gated-out point;

@@ -12,6 +12,7 @@ from .functional import (  # noqa: F401
     ms_deform_attn_forward,
     set_deterministic,
 )
+from .dcnv3 import DCNv3Function, dcnv3_backward, dcnv3_forward  # noqa: F401
 from .module import MultiScaleDeformableAttention  # noqa: F401
 
 __all__ = [
@@ -21,4 +22,7 @@ __all__ = [
     "ms_deform_attn_backward",
     "set_deterministic",
     "kernel_flags",
+    "DCNv3Function",
+    "dcnv3_forward",
+    "dcnv3_backward",
 ]

@@ -141,13 +141,13 @@ int64_t tile2d_bound(const Dims& d, int rpc) { return ((int64_t)d.S + rpc - 1) /
 // experiment knob (bits 16-17): CTA size of the TILED kernels; 0 = default
 int tiled_threads(unsigned flags) { return ((flags >> 16) & 3u) == 1u ? 512 : 1024; }
 
-template <int D, typename VT, int PT, int THREADS, int TILED, bool FUSED = false>
+template <int D, typename VT, int PT, int THREADS, int TILED, int PRE = 0>
 int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
-                    const void* loc, const void* w, void* out, msda::FusedArgs fa = msda::FusedArgs{nullptr, 0, 0.f}) {
+                    const void* loc, const void* w, void* out, msda::FusedArgs fa = msda::FusedArgs{}) {
   using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
   const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::fwd_row_words(NP, TILED == 1) * 4;
-  auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED, FUSED>;
+  auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED, PRE>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
@@ -161,14 +161,14 @@ int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int
   return MSDA_OK;
 }
 
-template <int D, typename VT, int PT, int THREADS, int TILED, typename ACC, bool FUSED = false>
+template <int D, typename VT, int PT, int THREADS, int TILED, typename ACC, int PRE = 0>
 int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
                     const int64_t* lsi, const void* loc, const void* w, ACC* gv, void* gl, void* gw,
-                    const msda::DetScale* det, msda::FusedArgs fa = msda::FusedArgs{nullptr, 0, 0.f}) {
+                    const msda::DetScale* det, msda::FusedArgs fa = msda::FusedArgs{}) {
   using G = msda::Geom<D, THREADS>;
   const int NP = d.L * d.P;
   const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::bwd_row_words(NP, TILED == 1) * 4;
-  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC, FUSED>;
+  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC, PRE>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
@@ -263,7 +263,7 @@ int bwd_fast_det(cudaStream_t st, const Dims& d, int dtype, const void* go, cons
 
 int fwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
               const void* off, const void* logits, void* out, msda::FusedArgs fa) {
-#define CALL_FF(D_, VT_, PT_) launch_fwd_fast<D_, VT_, PT_, 256, 0, true>(st, d, value, shapes, lsi, off, logits, out, fa)
+#define CALL_FF(D_, VT_, PT_) launch_fwd_fast<D_, VT_, PT_, 256, 0, msda::kPreFused>(st, d, value, shapes, lsi, off, logits, out, fa)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D_FUSED(float, CALL_FF);
   MSDA_DISPATCH_D_FUSED(__nv_bfloat16, CALL_FF);
 #undef CALL_FF
@@ -273,11 +273,42 @@ int bwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* go, const v
               const int64_t* lsi, const void* off, const void* logits, float* gv, void* goff, void* glog,
               msda::FusedArgs fa) {
 #define CALL_FB(D_, VT_, PT_)                                                                                    \
-  launch_bwd_fast<D_, VT_, PT_, 256, 2, float, true>(st, d, go, value, shapes, lsi, off, logits, gv, goff, glog, \
+  launch_bwd_fast<D_, VT_, PT_, 256, 2, float, msda::kPreFused>(st, d, go, value, shapes, lsi, off, logits, gv, goff, glog, \
                                                      nullptr, fa)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D_FUSED(float, CALL_FB);
   MSDA_DISPATCH_D_FUSED(__nv_bfloat16, CALL_FB);
 #undef CALL_FB
+}
+
+// DCNv3: runtime point count (K = kernel_h * kernel_w), LINEAR forward, STRIP backward
+#define MSDA_DISPATCH_D_DCN(VT_, CALL)                       \
+  do {                                                       \
+    switch (d.D) {                                           \
+      case 16: return CALL(16, VT_);                         \
+      case 32: return CALL(32, VT_);                         \
+      case 64: return CALL(64, VT_);                         \
+      case 128: return CALL(128, VT_);                       \
+      default: return fail(MSDA_ERR_UNSUPPORTED, "dcnv3: group_channels=%d", d.D); \
+    }                                                        \
+  } while (0)
+
+int fwd_dcn(cudaStream_t st, const Dims& d, int dtype, const void* input, const void* off, const void* mask, void* out,
+            msda::FusedArgs fa) {
+#define CALL_DF(D_, VT_) \
+  launch_fwd_fast<D_, VT_, 0, 256, 0, msda::kPreDcn>(st, d, input, nullptr, nullptr, off, mask, out, fa)
+  if (dtype == MSDA_F32) MSDA_DISPATCH_D_DCN(float, CALL_DF);
+  MSDA_DISPATCH_D_DCN(__nv_bfloat16, CALL_DF);
+#undef CALL_DF
+}
+
+int bwd_dcn(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* input, const void* off,
+            const void* mask, float* gi, void* goff, void* gmask, msda::FusedArgs fa) {
+#define CALL_DB(D_, VT_)                                                                                          \
+  launch_bwd_fast<D_, VT_, 0, 256, 2, float, msda::kPreDcn>(st, d, go, input, nullptr, nullptr, off, mask, gi, goff, \
+                                                            gmask, nullptr, fa)
+  if (dtype == MSDA_F32) MSDA_DISPATCH_D_DCN(float, CALL_DB);
+  MSDA_DISPATCH_D_DCN(__nv_bfloat16, CALL_DB);
+#undef CALL_DB
 }
 
 // ------------------------------------------------------------------------------------------
@@ -529,7 +560,10 @@ int msda_fused_forward(void* stream, const void* value, const int64_t* spatial_s
     return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
   DeviceGuard guard;
   MSDA_CUDA(guard.enter(value));
-  const msda::FusedArgs fa{reference_points, ref_dim, 1.0f / (float)num_point};
+  msda::FusedArgs fa{};
+  fa.ref = reference_points;
+  fa.ref_dim = ref_dim;
+  fa.inv_P = 1.0f / (float)num_point;
   return fwd_fused(static_cast<cudaStream_t>(stream), d, dtype, value, spatial_shapes, level_start_index,
                    sampling_offsets, attn_logits, output, fa);
 }
@@ -560,7 +594,10 @@ int msda_fused_backward(void* stream, const void* grad_output, const void* value
   float* gv32 = static_cast<float*>(grad_value);
   if (dtype == MSDA_BF16) gv32 = static_cast<float*>(workspace);
   MSDA_CUDA(cudaMemsetAsync(gv32, 0, (size_t)d.n_value() * sizeof(float), st));
-  const msda::FusedArgs fa{reference_points, ref_dim, 1.0f / (float)num_point};
+  msda::FusedArgs fa{};
+  fa.ref = reference_points;
+  fa.ref_dim = ref_dim;
+  fa.inv_P = 1.0f / (float)num_point;
   if (int s = bwd_fused(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_offsets,
                         attn_logits, gv32, grad_offsets, grad_logits, fa))
     return s;
@@ -568,6 +605,103 @@ int msda_fused_backward(void* stream, const void* grad_output, const void* value
     const int64_t n = d.n_value();
     msda::msda_cast_f32_to_bf16_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
         gv32, static_cast<__nv_bfloat16*>(grad_value), n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    MSDA_CUDA(cudaGetLastError());
+  }
+  return MSDA_OK;
+}
+
+namespace {
+// DCNv3 as an MSDeformAttn problem: value = input [N, H_in*W_in, G, C], one level, Q = H_out*W_out, P = K.
+int dcn_setup(int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w, int dilation_h,
+              int dilation_w, int group, int group_channels, float offset_scale, int batch, int height_in,
+              int width_in, int height_out, int width_out, int dtype, Dims* d, msda::FusedArgs* fa) {
+  if (kernel_h < 1 || kernel_w < 1 || stride_h < 1 || stride_w < 1 || dilation_h < 1 || dilation_w < 1 || pad_h < 0 ||
+      pad_w < 0 || batch < 0 || height_in < 0 || width_in < 0 || height_out < 0 || width_out < 0 || group < 1 ||
+      group_channels < 1)
+    return fail(MSDA_ERR_INVALID_ARGUMENT, "dcnv3: bad geometry");
+  *d = Dims{batch, height_in * width_in, group, group_channels, 1, height_out * width_out, kernel_h * kernel_w};
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16) return fail(MSDA_ERR_UNSUPPORTED, "dcnv3: float32 / bfloat16 only");
+  if (d->rows() * d->D != 0 && !fast_ok(*d, dtype, 0))
+    return fail(MSDA_ERR_UNSUPPORTED,
+                "dcnv3: needs group_channels in {16,32,64,128} and kernel_h*kernel_w <= 64 (got %d, %d)",
+                group_channels, kernel_h * kernel_w);
+  msda::FusedArgs a{};
+  a.kernel_h = kernel_h; a.kernel_w = kernel_w; a.stride_h = stride_h; a.stride_w = stride_w;
+  a.pad_h = pad_h; a.pad_w = pad_w; a.dil_h = dilation_h; a.dil_w = dilation_w;
+  a.height_in = height_in; a.width_in = width_in; a.width_out = width_out > 0 ? width_out : 1;
+  a.offset_scale = offset_scale;
+  *fa = a;
+  return MSDA_OK;
+}
+}  // namespace
+
+int msda_dcnv3_forward(void* stream, const void* input, const float* offset, const float* mask, int kernel_h,
+                       int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w, int dilation_h, int dilation_w,
+                       int group, int group_channels, float offset_scale, int batch, int height_in, int width_in,
+                       int height_out, int width_out, void* output, int dtype, unsigned flags) {
+  (void)flags;
+  g_err[0] = 0;
+  Dims d;
+  msda::FusedArgs fa;
+  if (int s = dcn_setup(kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, group,
+                        group_channels, offset_scale, batch, height_in, width_in, height_out, width_out, dtype, &d, &fa))
+    return s;
+  if (d.rows() * d.D == 0) return MSDA_OK;
+  if (!output) return fail(MSDA_ERR_INVALID_ARGUMENT, "output is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceGuard guard;
+  MSDA_CUDA(guard.enter(output));
+  if (d.S == 0) {
+    MSDA_CUDA(cudaMemsetAsync(output, 0, (size_t)(d.rows() * d.D) * elem_size(dtype), st));
+    return MSDA_OK;
+  }
+  if (!input || !offset || !mask) return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  return fwd_dcn(st, d, dtype, input, offset, mask, output, fa);
+}
+
+int msda_dcnv3_backward(void* stream, const void* grad_output, const void* input, const float* offset,
+                        const float* mask, int kernel_h, int kernel_w, int stride_h, int stride_w, int pad_h, int pad_w,
+                        int dilation_h, int dilation_w, int group, int group_channels, float offset_scale, int batch,
+                        int height_in, int width_in, int height_out, int width_out, void* grad_input,
+                        float* grad_offset, float* grad_mask, void* workspace, size_t workspace_bytes, int dtype,
+                        unsigned flags) {
+  (void)flags;
+  g_err[0] = 0;
+  Dims d;
+  msda::FusedArgs fa;
+  if (int s = dcn_setup(kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, group,
+                        group_channels, offset_scale, batch, height_in, width_in, height_out, width_out, dtype, &d, &fa))
+    return s;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d.n_value() == 0 && d.n_points() == 0) return MSDA_OK;
+  const void* anchor = d.n_value() ? grad_input : (const void*)grad_mask;
+  if (!anchor) return fail(MSDA_ERR_INVALID_ARGUMENT, "gradient output pointer is null");
+  DeviceGuard guard;
+  MSDA_CUDA(guard.enter(anchor));
+  const size_t need = dtype == MSDA_BF16 ? (size_t)d.n_value() * sizeof(float) : 0;
+  if (need && (!workspace || workspace_bytes < need))
+    return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, workspace_bytes);
+  float* gi32 = dtype == MSDA_BF16 ? static_cast<float*>(workspace) : static_cast<float*>(grad_input);
+  if (d.n_value()) {
+    if (!grad_input) return fail(MSDA_ERR_INVALID_ARGUMENT, "grad_input is null");
+    MSDA_CUDA(cudaMemsetAsync(gi32, 0, (size_t)d.n_value() * sizeof(float), st));
+    if (dtype == MSDA_BF16 && d.n_points() == 0)
+      MSDA_CUDA(cudaMemsetAsync(grad_input, 0, (size_t)d.n_value() * 2, st));
+  }
+  if (d.n_points() == 0) return MSDA_OK;
+  if (!grad_offset || !grad_mask) return fail(MSDA_ERR_INVALID_ARGUMENT, "grad_offset / grad_mask is null");
+  if (d.n_value() == 0) {
+    MSDA_CUDA(cudaMemsetAsync(grad_offset, 0, (size_t)d.n_points() * 2 * sizeof(float), st));
+    MSDA_CUDA(cudaMemsetAsync(grad_mask, 0, (size_t)d.n_points() * sizeof(float), st));
+    return MSDA_OK;
+  }
+  if (!grad_output || !input || !offset || !mask) return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  if (int s = bwd_dcn(st, d, dtype, grad_output, input, offset, mask, gi32, grad_offset, grad_mask, fa)) return s;
+  if (dtype == MSDA_BF16) {
+    const int64_t n = d.n_value();
+    msda::msda_cast_f32_to_bf16_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
+        gi32, static_cast<__nv_bfloat16*>(grad_input), n);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     MSDA_CUDA(cudaGetLastError());
   }

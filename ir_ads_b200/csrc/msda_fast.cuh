@@ -98,6 +98,20 @@ __device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes
   __syncthreads();
 }
 
+// DCNv3: a single level whose shape comes with the call, not from device tensors
+template <int TW, int TH>
+__device__ __forceinline__ void set_single_level(LevelTab* tab, int H, int W) {
+  if (threadIdx.x == 0) {
+    tab->H[0] = H;
+    tab->W[0] = W;
+    tab->start[0] = 0;
+    tab->tiles_x[0] = (W + TW - 1) / TW;
+    tab->tile_begin[0] = 0;
+    tab->total_tiles = tab->tiles_x[0] * ((H + TH - 1) / TH);
+  }
+  __syncthreads();
+}
+
 template <int PT>
 __device__ __forceinline__ int level_of(int pt, int P) {
   if constexpr (PT > 0) {
@@ -252,10 +266,36 @@ struct PointRec {
   float lw, lh;  // fractional parts; lw < 0 marks a gated-out point
 };
 
+// DCNv3 gives pixel coordinates directly (cuh:262-263 gate, :48-58 cell), no exact-product trick needed.
+__device__ __forceinline__ Cell<float> locate_pixel(float px, float py, int H, int W) {
+  Cell<float> c;
+  const bool ok = (py > -1.0f) && (px > -1.0f) && (py < (float)H) && (px < (float)W);
+  const float fy = floorf(py), fx = floorf(px);
+  c.y0 = ok ? (int)fy : 0;
+  c.x0 = ok ? (int)fx : 0;
+  c.lh = ok ? py - fy : 0.0f;
+  c.lw = ok ? px - fx : 0.0f;
+  unsigned v = 0;
+  if (ok) {
+    const bool y0ok = c.y0 >= 0, y1ok = c.y0 + 1 <= H - 1, x0ok = c.x0 >= 0, x1ok = c.x0 + 1 <= W - 1;
+    v = (unsigned)(y0ok && x0ok) | ((unsigned)(y0ok && x1ok) << 1) | ((unsigned)(y1ok && x0ok) << 2) |
+        ((unsigned)(y1ok && x1ok) << 3);
+  }
+  c.valid = v;
+  return c;
+}
+
+__device__ __forceinline__ PointRec record_from_cell(const Cell<float> c, float aw, int Hl, int Wl, int start, int H,
+                                                     int h, int D);
+
 __device__ __forceinline__ PointRec make_record(float x, float y, float aw, int Hl, int Wl, int start, int H, int h,
                                                 int D) {
+  return record_from_cell(locate<float>(x, y, Hl, Wl), aw, Hl, Wl, start, H, h, D);
+}
+
+__device__ __forceinline__ PointRec record_from_cell(const Cell<float> c, float aw, int Hl, int Wl, int start, int H,
+                                                     int h, int D) {
   PointRec r;
-  const Cell<float> c = locate<float>(x, y, Hl, Wl);
   const float hh = 1.0f - c.lh, hw = 1.0f - c.lw;
   r.cw.x = (c.valid & 1u) ? hh * hw * aw : 0.0f;
   r.cw.y = (c.valid & 2u) ? hh * c.lw * aw : 0.0f;
@@ -283,7 +323,18 @@ struct FusedArgs {
   const float* ref;   // reference_points [B, Q, L, ref_dim]
   int ref_dim;        // 2: loc = ref + off / (W_l, H_l);  4: loc = ref_xy + off / P * ref_wh * 0.5
   float inv_P;        // 1 / P
+  // PRE == 2 (DCNv3): the same gather/scatter core driven by a convolution-style
+  // sampling grid (detrex/layers/csrc/DCNv3/dcnv3_im2col_cuda.cuh:217-275): rows are (n, output pixel,
+  // group), the K = kernel_w*kernel_h points of a row sit at
+  //   loc_w = p0_w - (dil_w*(kw-1)/2)*scale + (i*dil_w + offset_w)*scale   (pixel units, i outer, j inner)
+  // `loc` holds the offsets [N, Ho, Wo, G*K*2], `w` the mask [N, Ho, Wo, G*K]; one level = the input map.
+  int kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+  int height_in, width_in, width_out;
+  float offset_scale;
 };
+// PRE: 0 = sampling_locations / attention_weights given (the reference operator), 1 = fused module chain,
+//      2 = DCNv3 sampling grid
+constexpr int kPrePlain = 0, kPreFused = 1, kPreDcn = 2;
 
 __device__ __forceinline__ float2 fused_location(const float2 off, const float* r, int ref_dim, int Hl, int Wl,
                                                  float inv_P) {
@@ -295,6 +346,20 @@ __device__ __forceinline__ float2 fused_location(const float2 off, const float* 
     loc.x = __fadd_rn(__ldg(r + 0), __fmul_rn(__fmul_rn(__fmul_rn(off.x, inv_P), __ldg(r + 2)), 0.5f));
     loc.y = __fadd_rn(__ldg(r + 1), __fmul_rn(__fmul_rn(__fmul_rn(off.y, inv_P), __ldg(r + 3)), 0.5f));
   }
+  return loc;
+}
+
+// DCNv3 sampling position of kernel point `pt` (= i*kernel_h + j, i over kernel_w) for output pixel q,
+// in input-pixel units (dcnv3_im2col_cuda.cuh:232-260).
+__device__ __forceinline__ float2 dcn_location(const float2 off, int pt, int q, const FusedArgs& a) {
+  const int wo = q % a.width_out, ho = q / a.width_out;
+  const int i = pt / a.kernel_h, j = pt - i * a.kernel_h;
+  const int cw = (a.dil_w * (a.kernel_w - 1)) >> 1, ch = (a.dil_h * (a.kernel_h - 1)) >> 1;
+  const float p0w = (float)(cw - a.pad_w + wo * a.stride_w) - (float)cw * a.offset_scale;
+  const float p0h = (float)(ch - a.pad_h + ho * a.stride_h) - (float)ch * a.offset_scale;
+  float2 loc;
+  loc.x = fmaf((float)(i * a.dil_w) + off.x, a.offset_scale, p0w);
+  loc.y = fmaf((float)(j * a.dil_h) + off.y, a.offset_scale, p0h);
   return loc;
 }
 
@@ -328,7 +393,7 @@ __device__ __forceinline__ float row_softmax(const float* logits_row, float* scr
 // TILED (persistent): software pipeline per warp -- wait for this item's raw loc/w in shared memory
 //   -> phase 1: records -> issue cp.async for the NEXT item's loc/w -> phase 2: gather (the long
 //   phase, hides the HBM latency of the copy).
-template <int D, typename VT, int PT, int THREADS, int ORDER, bool FUSED>
+template <int D, typename VT, int PT, int THREADS, int ORDER, int PRE>
 #ifndef MSDA_FWD_MINB
 #define MSDA_FWD_MINB 6
 #endif
@@ -341,14 +406,17 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   using G = Geom<D, THREADS>;
   constexpr int LANES = G::LANES;
   constexpr bool STAGED = (ORDER == 1);
-  static_assert(!(FUSED && STAGED), "the fused pre-op chain is built for the single-pass row orders");
+  constexpr bool FUSED = (PRE == kPreFused);
+  constexpr bool DCN = (PRE == kPreDcn);
+  static_assert(!(PRE != kPrePlain && STAGED), "the fused pre-op chains are built for the single-pass row orders");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
   const int row_words = fwd_row_words(NP, STAGED);
 
-  load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
+  if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
+  else load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
 
   const int sub = (threadIdx.x & 31) % LANES;            // lane inside the row
   const int rin = threadIdx.x / LANES;                   // row inside the CTA
@@ -392,7 +460,13 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
           } else {
             aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
           }
-          const PointRec r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+          PointRec r;
+          if constexpr (DCN) {
+            const float2 px = dcn_location(xy, pt, (int)((cur.row / H) % Q), fused);
+            r = record_from_cell(locate_pixel(px.x, px.y, tab->H[0], tab->W[0]), aw, tab->H[0], tab->W[0], 0, H, cur.h, D);
+          } else {
+            r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+          }
           s_cw[pt] = r.cw;
           s_oc[pt] = r.oc;
         }
@@ -522,7 +596,7 @@ __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
 #ifndef MSDA_BWD_MINB
 #define MSDA_BWD_MINB 4
 #endif
-template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC, bool FUSED>
+template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC, int PRE>
 __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_BWD_MINB : 1)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
@@ -534,14 +608,17 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   using G = Geom<D, THREADS>;
   constexpr int LANES = G::LANES;
   constexpr bool STAGED = (ORDER == 1);
-  static_assert(!(FUSED && STAGED), "the fused pre-op chain is built for the single-pass row orders");
+  constexpr bool FUSED = (PRE == kPreFused);
+  constexpr bool DCN = (PRE == kPreDcn);
+  static_assert(!(PRE != kPrePlain && STAGED), "the fused pre-op chains are built for the single-pass row orders");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
   const int row_words = bwd_row_words(NP, STAGED);
 
-  load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
+  if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
+  else load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
 
   const int sub = (threadIdx.x & 31) % LANES;
   const int rin = threadIdx.x / LANES;
@@ -593,7 +670,13 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           } else {
             aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
           }
-          const PointRec r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+          PointRec r;
+          if constexpr (DCN) {
+            const float2 px = dcn_location(xy, pt, (int)((cur.row / H) % Q), fused);
+            r = record_from_cell(locate_pixel(px.x, px.y, tab->H[0], tab->W[0]), aw, tab->H[0], tab->W[0], 0, H, cur.h, D);
+          } else {
+            r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+          }
           cw = r.cw;
           fin = make_int4(r.oc, __float_as_int(r.lw), __float_as_int(r.lh), __float_as_int(aw));
         }
@@ -680,8 +763,15 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           const float hh = 1.0f - lh, hw = 1.0f - lw;
           const int l = level_of<PT>(mine, P);
           g_aw = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;
-          g_x = (hh * (d1 - d0) + lh * (d3 - d2)) * aw * (float)tab->W[l];
-          g_y = (hw * (d2 - d0) + lw * (d3 - d1)) * aw * (float)tab->H[l];
+          g_x = (hh * (d1 - d0) + lh * (d3 - d2)) * aw;    // d / d(pixel coordinate)
+          g_y = (hw * (d2 - d0) + lw * (d3 - d1)) * aw;
+          if constexpr (DCN) {                                // offsets are in pixels x offset_scale (dcnv3 cuh:150-157)
+            g_x *= fused.offset_scale;
+            g_y *= fused.offset_scale;
+          } else {                                            // locations are normalised by the level size
+            g_x *= (float)tab->W[l];
+            g_y *= (float)tab->H[l];
+          }
         }
         if constexpr (FUSED) {
           // chain rule through loc = ref + off / (W,H)   or   ref_xy + off / P * ref_wh * 0.5

@@ -72,3 +72,44 @@ def forward_backward(value, shapes, lsi, loc, w, grad_out):
     out = forward(value, shapes, lsi, loc, w)
     gv, gl, gw = backward(grad_out.contiguous(), value, shapes, lsi, loc, w)
     return out, gv, gl, gw
+
+
+# ---------------------------------------------------------------------------------------------
+# DCNv3: the reference's own kernels (oracle/_ref/libdcnv3_refcuda.so), float32 only
+# ---------------------------------------------------------------------------------------------
+DCN_LIB_PATH = os.path.join(_HERE, "_ref", "libdcnv3_refcuda.so")
+_dcn = None
+
+
+def dcn_available() -> bool:
+    return os.path.exists(DCN_LIB_PATH)
+
+
+def _dcn_lib():
+    global _dcn
+    if _dcn is None:
+        _dcn = ctypes.CDLL(DCN_LIB_PATH)
+        _dcn.dcnv3_ref_forward.restype = ctypes.c_int
+        _dcn.dcnv3_ref_backward.restype = ctypes.c_int
+    return _dcn
+
+
+def dcnv3_forward_backward(input, offset, mask, grad_out, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                           dilation_h, dilation_w, group, group_channels, offset_scale, backward=True):
+    N, H, W, _ = input.shape
+    _, Ho, Wo, _ = offset.shape
+    geom = [ctypes.c_int(int(x)) for x in (kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
+                                           group, group_channels, N, H, W, Ho, Wo)]
+    st = ctypes.c_void_p(torch.cuda.current_stream(input.device).cuda_stream)
+    out = torch.zeros((N, Ho, Wo, group * group_channels), dtype=torch.float32, device=input.device)
+    err = _dcn_lib().dcnv3_ref_forward(_p(input), _p(offset), _p(mask), _p(out), *geom, ctypes.c_float(offset_scale), st)
+    if err:
+        raise RuntimeError(f"reference dcnv3 forward: cuda error {err}")
+    if not backward:
+        return out
+    gi, go, gm = torch.zeros_like(input), torch.zeros_like(offset), torch.zeros_like(mask)
+    err = _dcn_lib().dcnv3_ref_backward(_p(grad_out.contiguous()), _p(input), _p(offset), _p(mask), *geom,
+                                        ctypes.c_float(offset_scale), _p(gi), _p(go), _p(gm), st)
+    if err:
+        raise RuntimeError(f"reference dcnv3 backward: cuda error {err}")
+    return out, gi, go, gm
