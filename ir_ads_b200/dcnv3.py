@@ -110,3 +110,111 @@ class DCNv3Function(Function):
         gi, go, gm = dcnv3_backward(input, offset.float(), mask.float(), *ctx.args, grad_output.to(input.dtype),
                                     ctx.im2col_step)
         return (gi.to(ctx.in_dtype), go.to(offset.dtype), gm.to(mask.dtype)) + (None,) * 12
+
+
+# ------------------------------------------------------------------------------------------------
+# the DCNv3 operator module (InternImage), same constructor / parameter names as the reference
+# (/root/reference/detrex/layers/dcn_v3.py:373-500) so InternImage checkpoints load
+# ------------------------------------------------------------------------------------------------
+import torch.nn as nn  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+
+class _Permute(nn.Module):
+    def __init__(self, *dims):
+        super().__init__()
+        self.dims = dims
+
+    def forward(self, x):
+        return x.permute(*self.dims)
+
+
+def _norm_layer(dim, kind, in_format, out_format, eps=1e-6):
+    """Sequential with the reference's slot layout (dcn_v3.py:192-214), so ``dw_conv.1.<k>.weight`` keys match."""
+    layers = []
+    if kind == "BN":
+        if in_format == "channels_last":
+            layers.append(_Permute(0, 3, 1, 2))
+        layers.append(nn.BatchNorm2d(dim))
+        if out_format == "channels_last":
+            layers.append(_Permute(0, 2, 3, 1))
+    elif kind == "LN":
+        if in_format == "channels_first":
+            layers.append(_Permute(0, 2, 3, 1))
+        layers.append(nn.LayerNorm(dim, eps=eps))
+        if out_format == "channels_first":
+            layers.append(_Permute(0, 3, 1, 2))
+    else:
+        raise NotImplementedError(f"norm layer {kind!r}")
+    return nn.Sequential(*layers)
+
+
+def _act_layer(kind):
+    if kind == "ReLU":
+        return nn.ReLU(inplace=True)
+    if kind == "SiLU":
+        return nn.SiLU(inplace=True)
+    if kind == "GELU":
+        return nn.GELU()
+    raise NotImplementedError(f"activation {kind!r}")
+
+
+class DCNv3(nn.Module):
+    """input (N, H, W, C) -> output (N, H, W, C): input projection, depth-wise conv branch producing offsets and
+    softmax-normalised masks per group, the DCNv3 core op, optional centre-feature blending, output projection."""
+
+    def __init__(self, channels=64, kernel_size=3, dw_kernel_size=None, stride=1, pad=1, dilation=1, group=4,
+                 offset_scale=1.0, act_layer="GELU", norm_layer="LN", center_feature_scale=False):
+        super().__init__()
+        if channels % group != 0:
+            raise ValueError(f"channels must be divisible by group, but got {channels} and {group}")
+        dw_kernel_size = dw_kernel_size if dw_kernel_size is not None else kernel_size
+        self.offset_scale = offset_scale
+        self.channels = channels
+        self.kernel_size = kernel_size
+        self.dw_kernel_size = dw_kernel_size
+        self.stride = stride
+        self.dilation = dilation
+        self.pad = pad
+        self.group = group
+        self.group_channels = channels // group
+        self.center_feature_scale = center_feature_scale
+        self.dw_conv = nn.Sequential(
+            nn.Conv2d(channels, channels, kernel_size=dw_kernel_size, stride=1, padding=(dw_kernel_size - 1) // 2,
+                      groups=channels),
+            _norm_layer(channels, norm_layer, "channels_first", "channels_last"),
+            _act_layer(act_layer))
+        self.offset = nn.Linear(channels, group * kernel_size * kernel_size * 2)
+        self.mask = nn.Linear(channels, group * kernel_size * kernel_size)
+        self.input_proj = nn.Linear(channels, channels)
+        self.output_proj = nn.Linear(channels, channels)
+        self._reset_parameters()
+        if center_feature_scale:
+            self.center_feature_scale_proj_weight = nn.Parameter(torch.zeros((group, channels), dtype=torch.float))
+            self.center_feature_scale_proj_bias = nn.Parameter(torch.zeros((group,), dtype=torch.float))
+
+    def _reset_parameters(self):
+        for lin in (self.offset, self.mask):
+            nn.init.constant_(lin.weight.data, 0.0)
+            nn.init.constant_(lin.bias.data, 0.0)
+        for lin in (self.input_proj, self.output_proj):
+            nn.init.xavier_uniform_(lin.weight.data)
+            nn.init.constant_(lin.bias.data, 0.0)
+
+    def forward(self, input):
+        N, H, W, _ = input.shape
+        x = self.input_proj(input)
+        x_proj = x
+        dtype = x.dtype
+        x1 = self.dw_conv(input.permute(0, 3, 1, 2))
+        offset = self.offset(x1)
+        mask = F.softmax(self.mask(x1).reshape(N, H, W, self.group, -1), -1).reshape(N, H, W, -1).type(dtype)
+        x = DCNv3Function.apply(x.contiguous(), offset.contiguous(), mask.contiguous(), self.kernel_size,
+                                self.kernel_size, self.stride, self.stride, self.pad, self.pad, self.dilation,
+                                self.dilation, self.group, self.group_channels, self.offset_scale, 256)
+        if self.center_feature_scale:
+            scale = F.linear(x1, weight=self.center_feature_scale_proj_weight,
+                             bias=self.center_feature_scale_proj_bias).sigmoid()
+            scale = scale[..., None].repeat(1, 1, 1, 1, self.channels // self.group).flatten(-2)
+            x = x * (1 - scale) + x_proj * scale
+        return self.output_proj(x)

@@ -76,6 +76,12 @@ def test_public_surface_matches_reference():
     assert list(asig.parameters) == ["ctx", "value", "value_spatial_shapes", "value_level_start_index",
                                      "sampling_locations", "attention_weights", "im2col_step"]
     assert callable(ir_ads_b200.ms_deform_attn_forward) and callable(ir_ads_b200.ms_deform_attn_backward)
+    # the detrex._C replacement exposes exactly the four functions of csrc/vision.cpp:54-59
+    from ir_ads_b200 import _C
+    assert sorted(_C.__all__) == ["dcnv3_backward", "dcnv3_forward", "ms_deform_attn_backward", "ms_deform_attn_forward"]
+    assert list(inspect.signature(_C.ms_deform_attn_backward).parameters) == [
+        "value", "spatial_shapes", "level_start_index", "sampling_loc", "attn_weight", "grad_output", "im2col_step"]
+    assert list(inspect.signature(_C.dcnv3_forward).parameters)[:4] == ["input", "offset", "mask", "kernel_h"]
 
 
 def test_module_parameters_and_init():

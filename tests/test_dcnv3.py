@@ -142,3 +142,40 @@ def test_against_reference_dcnv3_cuda_kernels():
             # grad_offset needs no boundary mask
             err = (a - b).abs().max().item()
             assert err <= 1e-5 * b.abs().max().item() + 1e-6, (key, stride, err)
+
+
+def test_dcnv3_module_parameter_layout():
+    from ir_ads_b200.dcnv3 import DCNv3
+    m = DCNv3(channels=64, group=4, center_feature_scale=True)
+    keys = list(m.state_dict())
+    for k in ("dw_conv.0.weight", "dw_conv.1.1.weight", "offset.weight", "mask.bias", "input_proj.weight",
+              "output_proj.bias", "center_feature_scale_proj_weight", "center_feature_scale_proj_bias"):
+        assert k in keys, k
+    assert m.offset.weight.abs().sum() == 0 and m.mask.bias.abs().sum() == 0
+    with pytest.raises(ValueError):
+        DCNv3(channels=30, group=4)
+
+
+@pytest.mark.gpu
+def test_dcnv3_module_matches_port_composition():
+    """Module on the GPU vs the same parameters around the oracle port on the CPU in float64."""
+    from ir_ads_b200.dcnv3 import DCNv3
+    torch.manual_seed(0)
+    m = DCNv3(channels=64, group=4, center_feature_scale=True)
+    with torch.no_grad():
+        m.offset.weight.normal_(0, 0.3)
+        m.mask.weight.normal_(0, 0.3)
+        m.center_feature_scale_proj_weight.normal_(0, 0.1)
+    x = torch.randn(2, 11, 13, 64)
+    md = m.double()
+    xd = x.double()
+    x1 = md.dw_conv(xd.permute(0, 3, 1, 2))
+    off = md.offset(x1)
+    mask = torch.softmax(md.mask(x1).reshape(2, 11, 13, 4, -1), -1).reshape(2, 11, 13, -1)
+    xp = md.input_proj(xd)
+    core = dcnv3_torch.forward(xp, off, mask, 3, 3, 1, 1, 1, 1, 1, 1, 4, 16, 1.0)
+    sc = torch.nn.functional.linear(x1, md.center_feature_scale_proj_weight, md.center_feature_scale_proj_bias).sigmoid()
+    sc = sc[..., None].repeat(1, 1, 1, 1, 16).flatten(-2)
+    want = md.output_proj(core * (1 - sc) + xp * sc).detach()
+    got = m.float().to("cuda:0")(x.to("cuda:0")).detach().cpu().double()
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max() + 1e-6
