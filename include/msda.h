@@ -76,7 +76,7 @@ extern "C" {
 #define MSDA_FLAG_ORDER_LINEAR (1u << 2)  /* rows processed in memory order (the default)              */
 /* Encoder form only (Q == S): persistent CTAs walk (image, pyramid tile, head) work items so that a
  * tile's gather footprint stays in L1.  Same results; measured slower than LINEAR so far,
- * hence opt-in.  Bits 16-17 are an unstable tuning knob of these kernels (CTA size). */
+ * hence opt-in. */
 #define MSDA_FLAG_ORDER_TILED (1u << 3)
 /* One CTA = a strip of consecutive queries of ONE head (any Q): x-adjacent queries re-use corner lines in L1. */
 #define MSDA_FLAG_ORDER_STRIP (1u << 4)

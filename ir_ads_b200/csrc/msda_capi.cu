@@ -138,8 +138,6 @@ bool use_tile2d(const Dims& d, unsigned flags) {
 // device): sum_l ceil(H_l/TH)*ceil(W_l/TW) is ~1.03 * S/RPC for image pyramids; 25 % + 32 tiles per level of
 // slack covers them, the kernel's grid-stride step covers anything else.
 int64_t tile2d_bound(const Dims& d, int rpc) { return ((int64_t)d.S + rpc - 1) / rpc * 5 / 4 + 32 * (int64_t)d.L; }
-// experiment knob (bits 16-17): CTA size of the TILED kernels; 0 = default
-int tiled_threads(unsigned flags) { return ((flags >> 16) & 3u) == 1u ? 512 : 1024; }
 
 template <int D, typename VT, int PT, int THREADS, int TILED, int PRE = 0>
 int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
@@ -187,7 +185,6 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
     if (use_tile2d(d, flags)) return CALL(D_, VT_, PT_, 256, 3);                     \
     if (use_strip(d, flags)) return CALL(D_, VT_, PT_, 256, 2);                      \
     if (!use_tiled(d, flags)) return CALL(D_, VT_, PT_, 256, 0);                     \
-    if (tiled_threads(flags) == 512) return CALL(D_, VT_, PT_, 512, 1);              \
     return CALL(D_, VT_, PT_, 1024, 1);                                              \
   } while (0)
 

@@ -152,7 +152,7 @@ def test_fast_and_generic_kernels_agree(D, L, P, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("D,P,threads_knob", [(32, 4, 0), (32, 4, 1), (64, 4, 0), (16, 8, 1), (128, 2, 0), (32, 3, 0)])
+@pytest.mark.parametrize("D,P,threads_knob", [(32, 4, 0), (64, 4, 0), (16, 8, 0), (128, 2, 0), (32, 3, 0)])
 def test_tiled_and_linear_row_orders_agree(D, P, threads_knob, dtype):
     """The opt-in persistent TILED kernels (encoder form, Q == S) must give the same forward as the
     default LINEAR order bit for bit (same per-row arithmetic) and the same gradients up to atomic
