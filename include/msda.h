@@ -70,8 +70,14 @@ extern "C" {
  * (integer atomics commute, float atomics do not) with a power-of-two scale derived from
  * max|grad_output| * max|attn_weight|, then converted once: run-to-run identical, absolute error
  * <= 2^-38 of that bound per contribution, headroom for 2^25 maximal contributions per element.
+ * On the fast shapes the accumulation is a sorted segment reduction (points binned by bilinear cell, one
+ * lane group per output pixel gathers its bins and sums in registers: no atomics on grad_value, no
+ * zero-fill); elsewhere 64-bit integer reds.  Both produce identical bits.
  * grad_sampling_loc / grad_attn_weight are reproducible in every mode (fixed reduction order). */
 #define MSDA_FLAG_DETERMINISTIC (1u << 0)
+/* With MSDA_FLAG_DETERMINISTIC: use the fixed-point RED path even where the sorted segment reduction
+ * (msda_det.cuh) is available (A/B testing; both give the same bits). */
+#define MSDA_FLAG_DET_ATOMIC (1u << 6)
 #define MSDA_FLAG_FORCE_GENERIC (1u << 1) /* bypass the D in {16,32,64,128} fast kernels             */
 #define MSDA_FLAG_ORDER_LINEAR (1u << 2)  /* rows processed in memory order (the default)              */
 /* Encoder form only (Q == S): persistent CTAs walk (image, pyramid tile, head) work items so that a

@@ -24,6 +24,7 @@ FLAG_ORDER_LINEAR = 1 << 2
 FLAG_ORDER_TILED = 1 << 3
 FLAG_ORDER_STRIP = 1 << 4
 FLAG_ORDER_TILE2D = 1 << 5
+FLAG_DET_ATOMIC = 1 << 6
 ABI_VERSION = 1
 
 _lock = threading.Lock()

@@ -17,6 +17,7 @@
 
 #include "msda_fast.cuh"
 #include "msda_generic.cuh"
+#include "msda_det.cuh"
 
 namespace {
 
@@ -33,6 +34,7 @@ int fail(int status, const char* fmt, ...) {
 }
 
 int cuda_fail(cudaError_t e, const char* what) {
+  cudaGetLastError();   // clear the runtime's sticky last-error so it cannot be blamed on a later, healthy launch
   return fail(MSDA_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
@@ -125,7 +127,14 @@ cudaError_t persistent_grid(K kernel, int threads, size_t smem, unsigned* grid) 
 
 // Row order: TILED needs query i == pixel i of the pyramid (encoder self-attention, Q == S).
 bool use_tiled(const Dims& d, unsigned flags) {
-  return d.Q == d.S && (flags & MSDA_FLAG_ORDER_TILED) && !(flags & MSDA_FLAG_ORDER_LINEAR);
+  if (!(d.Q == d.S && (flags & MSDA_FLAG_ORDER_TILED) && !(flags & MSDA_FLAG_ORDER_LINEAR))) return false;
+  // the persistent 1024-thread CTAs stage records + raw loc/w for 4096/D rows; the row order is only a
+  // scheduling choice, so fall back to the default order when that does not fit in shared memory
+  const int NP = d.L * d.P, rpc = 1024 / (d.D / 4);
+  const size_t words = (size_t)rpc * (size_t)(msda::bwd_row_words(NP, true) > msda::fwd_row_words(NP, true)
+                                                  ? msda::bwd_row_words(NP, true)
+                                                  : msda::fwd_row_words(NP, true));
+  return sizeof(msda::LevelTab) + words * 4 <= 200 * 1024;
 }
 bool use_strip(const Dims& d, unsigned flags) {
   (void)d;
@@ -238,6 +247,70 @@ int bwd_fast_det(cudaStream_t st, const Dims& d, int dtype, const void* go, cons
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
 #undef CALL_BWD
+}
+
+// sorted deterministic path: backward without the scatter (grad_loc / grad_w only), LINEAR order
+int bwd_fast_noscatter(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value,
+                       const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, void* gl, void* gw) {
+  const unsigned flags = MSDA_FLAG_ORDER_LINEAR;
+#define CALL_BWD(D_, VT_, PT_, TH_, TL_)                                                                       \
+  launch_bwd_fast<D_, VT_, PT_, 256, 0, msda::NoScatter>(st, d, go, value, shapes, lsi, loc, w,                  \
+                                                         (msda::NoScatter*)nullptr, gl, gw, nullptr)
+  if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
+  MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
+#undef CALL_BWD
+}
+
+template <typename VT>
+int det_gather(cudaStream_t st, const Dims& d, const void* go, const int4* entries, const int* bin_start,
+               const int64_t* shapes, const int64_t* lsi, const msda::DetScale* scale, void* gv) {
+  const int64_t items = (int64_t)d.B * d.S * d.H;
+#define CALL_G(D_)                                                                                            \
+  do {                                                                                                        \
+    constexpr int RPC = 256 / (D_ / 4);                                                                       \
+    msda::det_gather_kernel<D_, VT><<<(unsigned)((items + RPC - 1) / RPC), 256, 0, st>>>(                     \
+        (const VT*)go, entries, bin_start, shapes, lsi, scale, (VT*)gv, d.B, d.S, d.H, d.L);                  \
+  } while (0)
+  switch (d.D) {
+    case 16: CALL_G(16); break;
+    case 32: CALL_G(32); break;
+    case 64: CALL_G(64); break;
+    case 128: CALL_G(128); break;
+    default: return fail(MSDA_ERR_UNSUPPORTED, "det gather: D=%d", d.D);
+  }
+#undef CALL_G
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MSDA_CUDA(cudaGetLastError());
+  return MSDA_OK;
+}
+
+// Workspace of the sorted deterministic path (all 16-byte aligned):
+//   [bins+1 ints: counts -> starts][bins ints: cursors][scan block sums][entries: n_points x 16 B][amax x2, DetScale]
+struct DetLayout {
+  int64_t bins;        // upper bound, B*H*(2S+2L)
+  int64_t n_scan;      // bins + 1
+  int64_t scan_blocks;
+  size_t off_cursor, off_sums, off_entries, off_misc, total;
+};
+DetLayout det_layout(const Dims& d) {
+  DetLayout l;
+  l.bins = (int64_t)d.B * d.H * msda::det_cells_bound(d.S, d.L);
+  l.n_scan = l.bins + 1;
+  l.scan_blocks = (l.n_scan + msda::kScanPerBlock - 1) / msda::kScanPerBlock;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  l.off_cursor = up((size_t)l.n_scan * 4);
+  l.off_sums = l.off_cursor + up((size_t)l.bins * 4);
+  l.off_entries = l.off_sums + up((size_t)l.scan_blocks * 4);
+  l.off_misc = l.off_entries + up((size_t)d.n_points() * 16);
+  l.total = l.off_misc + 256;
+  return l;
+}
+// the sorted path needs 32-bit bin / entry / row indices
+bool det_sorted_ok(const Dims& d, int dtype, unsigned flags) {
+  if (flags & MSDA_FLAG_DET_ATOMIC) return false;
+  if (!fast_ok(d, dtype, flags)) return false;
+  const int64_t lim = ((int64_t)1 << 31) - 4096;
+  return (int64_t)d.B * d.H * msda::det_cells_bound(d.S, d.L) < lim && d.n_points() < lim && d.rows() < lim;
 }
 
 // fused pre-op chain: single-pass row orders only (LINEAR forward, STRIP backward)
@@ -413,8 +486,11 @@ size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads,
   (void)num_levels; (void)num_query; (void)num_point;
   if (batch <= 0 || spatial_size <= 0 || num_heads <= 0 || channels <= 0) return 0;
   const size_t n_value = (size_t)batch * spatial_size * num_heads * channels;
-  // deterministic: 64-bit fixed-point accumulators + {amax bits x2, DetScale}
-  if (flags & MSDA_FLAG_DETERMINISTIC) return n_value * sizeof(long long) + 64;
+  if (flags & MSDA_FLAG_DETERMINISTIC) {
+    const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+    if (det_sorted_ok(d, dtype, flags)) return det_layout(d).total;   // bins, cursors, scan sums, entries
+    return n_value * sizeof(long long) + 64;   // 64-bit fixed-point accumulators + {amax bits x2, DetScale}
+  }
   // bf16 grad_value is accumulated in float and converted at the end
   if (dtype == MSDA_BF16) return n_value * sizeof(float);
   return 0;
@@ -460,10 +536,18 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
   if (det) {
     // ---- bit-reproducible grad_value: 64-bit fixed-point accumulation (see include/msda.h) ----
     const int64_t nv = d.n_value(), n_out = d.rows() * d.D, n_pts = d.n_points();
+    const bool sorted = det_sorted_ok(d, dtype, flags);
+    const DetLayout lay = sorted ? det_layout(d) : DetLayout{};
+    char* ws = static_cast<char*>(workspace);
     auto* acc = static_cast<unsigned long long*>(workspace);
-    auto* amax = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + (size_t)nv * 8);
-    auto* scale = reinterpret_cast<msda::DetScale*>(static_cast<char*>(workspace) + (size_t)nv * 8 + 16);
-    MSDA_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    auto* amax = reinterpret_cast<unsigned*>(ws + (sorted ? lay.off_misc : (size_t)nv * 8));
+    auto* scale = reinterpret_cast<msda::DetScale*>(reinterpret_cast<char*>(amax) + 16);
+    if (sorted) {   // zero the bins, cursors and {amax, scale}; entries are fully overwritten
+      MSDA_CUDA(cudaMemsetAsync(ws, 0, lay.off_sums, st));
+      MSDA_CUDA(cudaMemsetAsync(ws + lay.off_misc, 0, 256, st));
+    } else {
+      MSDA_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    }
     const int g_out = grid_for(n_out, 256, 148 * 8), g_pts = grid_for(n_pts, 256, 148 * 8);
     if (dtype == MSDA_F32) msda::msda_amax_kernel<float><<<g_out, 256, 0, st>>>((const float*)grad_output, n_out, amax);
     else if (dtype == MSDA_F64) msda::msda_amax_kernel<double><<<g_out, 256, 0, st>>>((const double*)grad_output, n_out, amax);
@@ -475,6 +559,36 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
     msda::msda_det_scale_kernel<<<1, 1, 0, st>>>(amax, scale, dtype == MSDA_F64 ? 44 : 38);
     count();
     MSDA_CUDA(cudaGetLastError());
+    if (sorted) {
+      // sorted segment reduction (msda_det.cuh): count -> scan -> fill -> gather; no atomics on grad_value
+      int* bins = reinterpret_cast<int*>(ws);
+      int* cursor = reinterpret_cast<int*>(ws + lay.off_cursor);
+      int* sums = reinterpret_cast<int*>(ws + lay.off_sums);
+      int4* entries = reinterpret_cast<int4*>(ws + lay.off_entries);
+      const float* loc = static_cast<const float*>(sampling_loc);
+      const float* w = static_cast<const float*>(attn_weight);
+      const int g_bin = grid_for(n_pts, 256, 148 * 32);
+      msda::det_bin_kernel<false><<<g_bin, 256, 0, st>>>(loc, w, spatial_shapes, level_start_index, d.H, d.L, d.Q, d.P,
+                                                         n_pts, bins, nullptr, nullptr);
+      count();
+      msda::det_scan_block_kernel<<<(unsigned)lay.scan_blocks, 256, 0, st>>>(bins, bins, sums, lay.n_scan);
+      count();
+      msda::det_scan_sums_kernel<<<1, 1024, 0, st>>>(sums, (int)lay.scan_blocks);
+      count();
+      msda::det_scan_add_kernel<<<(unsigned)lay.scan_blocks, 256, 0, st>>>(bins, sums, lay.n_scan);
+      count();
+      msda::det_bin_kernel<true><<<g_bin, 256, 0, st>>>(loc, w, spatial_shapes, level_start_index, d.H, d.L, d.Q, d.P,
+                                                        n_pts, cursor, bins, entries);
+      count();
+      MSDA_CUDA(cudaGetLastError());
+      if (int s2 = bwd_fast_noscatter(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                                      attn_weight, grad_sampling_loc, grad_attn_weight))
+        return s2;
+      if (dtype == MSDA_F32)
+        return det_gather<float>(st, d, grad_output, entries, bins, spatial_shapes, level_start_index, scale, grad_value);
+      return det_gather<__nv_bfloat16>(st, d, grad_output, entries, bins, spatial_shapes, level_start_index, scale,
+                                       grad_value);
+    }
     int s;
     if (fast_ok(d, dtype, flags))
       s = bwd_fast_det(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,

@@ -1,0 +1,211 @@
+// msda_det.cuh -- deterministic grad_value by sorted segment reduction (MSDA_FLAG_DETERMINISTIC, fast shapes).
+//
+// The atomic backward scatters 4 corner rows per sampling point into grad_value; float reds make the
+// rounding depend on arrival order.  This path removes the scatter altogether:
+//   1. det_bin_kernel<false>  every point finds its bilinear cell (same coordinate code as the other
+//                             kernels) and counts itself in that cell's bin
+//   2. scan (3 small kernels) bin counts -> bin start offsets
+//   3. det_bin_kernel<true>   every point writes a 16-byte entry {row, lw, lh, attention weight} into its bin
+//   4. det_gather_kernel      one lane group per (image, pixel, head): walks the (up to) four bins whose
+//                             cells have this pixel as a corner, gathers grad_out rows and accumulates in
+//                             64-bit fixed point IN REGISTERS, writes the pixel's D channels once.
+// Bins are filled in arbitrary order (an atomic cursor), but integer accumulation is order independent,
+// so the result is bit-reproducible -- and bit-identical to the fixed-point reds of the generic
+// deterministic path (same products, same scale).  No atomics touch grad_value, no zero-fill is needed.
+// grad_sampling_loc / grad_attn_weight come from the regular backward kernel with the scatter compiled
+// out (ACC = NoScatter).
+//
+// Cells live on the extended grid (H_l+1) x (W_l+1) of every level (the low corner of a cell can be -1),
+// bins are indexed [image][head][level cells].
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "msda_coords.cuh"
+#include "msda_fast.cuh"
+
+namespace msda {
+
+struct CellTab {
+  int H[kFastMaxLevels];
+  int W[kFastMaxLevels];
+  int start[kFastMaxLevels];
+  int cell_begin[kFastMaxLevels];   // first bin of the level inside one (image, head) block
+  int cells_per_bh;
+  int pad[3];
+};
+
+__device__ __forceinline__ void load_cell_tab(CellTab* t, const int64_t* shapes, const int64_t* lsi, int L) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int l = 0; l < L; ++l) {
+      t->H[l] = (int)shapes[2 * l];
+      t->W[l] = (int)shapes[2 * l + 1];
+      t->start[l] = (int)lsi[l];
+      t->cell_begin[l] = acc;
+      acc += (t->H[l] + 1) * (t->W[l] + 1);
+    }
+    t->cells_per_bh = acc;
+  }
+  __syncthreads();
+}
+
+// upper bound of bins per (image, head) that needs only S and L: (H+1)(W+1) <= 2HW + 2
+__host__ __device__ constexpr int64_t det_cells_bound(int64_t S, int64_t L) { return 2 * S + 2 * L; }
+
+// FILL == false: count points per bin.  FILL == true: write entries (bins already scanned into `bin_start`).
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+det_bin_kernel(const float* __restrict__ loc, const float* __restrict__ w, const int64_t* __restrict__ shapes,
+               const int64_t* __restrict__ lsi, int H, int L, int Q, int P, int64_t n_points, int* __restrict__ counter,
+               const int* __restrict__ bin_start, int4* __restrict__ entries) {
+  __shared__ CellTab tab;
+  load_cell_tab(&tab, shapes, lsi, L);
+  const int NP = L * P;
+  for (int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pt < n_points;
+       pt += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = pt / NP;
+    const int l = (int)(pt - row * NP) / P;
+    const int h = (int)(row % H);
+    const int64_t b = row / H / Q;
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pt);
+    const Cell<float> c = locate<float>(xy.x, xy.y, tab.H[l], tab.W[l]);
+    if (c.valid == 0u) continue;
+    const int64_t bin = (b * H + h) * (int64_t)tab.cells_per_bh + tab.cell_begin[l] + (c.y0 + 1) * (tab.W[l] + 1) + (c.x0 + 1);
+    if (!FILL) {
+      atomicAdd(counter + bin, 1);
+    } else {
+      const int pos = bin_start[bin] + atomicAdd(counter + bin, 1);
+      entries[pos] = make_int4((int)row, __float_as_int(c.lw), __float_as_int(c.lh), __float_as_int(__ldg(w + pt)));
+    }
+  }
+}
+
+// ---- exclusive scan of n ints, 2048 per block --------------------------------------------------------
+constexpr int kScanPerBlock = 2048;
+
+__global__ void __launch_bounds__(256) det_scan_block_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                           int* __restrict__ block_sums, int64_t n) {
+  __shared__ int warp_tot[8];
+  const int64_t base = (int64_t)blockIdx.x * kScanPerBlock + threadIdx.x * 8;
+  int v[8], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    sum += v[k];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  int off = 0;
+  for (int k = 0; k < warp; ++k) off += warp_tot[k];
+  int run = off + inc - sum;   // exclusive prefix of this thread's first element inside the block
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == 255) block_sums[blockIdx.x] = run;
+}
+
+__global__ void __launch_bounds__(1024) det_scan_sums_kernel(int* __restrict__ block_sums, int n_blocks) {
+  __shared__ int part[1024];
+  const int per = (n_blocks + 1023) / 1024;
+  const int b0 = threadIdx.x * per;
+  int sum = 0;
+  for (int k = 0; k < per; ++k)
+    if (b0 + k < n_blocks) sum += block_sums[b0 + k];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int k = 0; k < 1024; ++k) {
+      const int t = part[k];
+      part[k] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int k = 0; k < per; ++k)
+    if (b0 + k < n_blocks) {
+      const int t = block_sums[b0 + k];
+      block_sums[b0 + k] = run;
+      run += t;
+    }
+}
+
+__global__ void __launch_bounds__(256) det_scan_add_kernel(int* __restrict__ out, const int* __restrict__ block_sums,
+                                                         int64_t n) {
+  const int64_t base = (int64_t)blockIdx.x * kScanPerBlock + threadIdx.x * 8;
+  const int off = block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (base + k < n) out[base + k] += off;
+}
+
+// ---- gather: one LANES-wide lane group per (image, pixel, head) -----------------------------------------
+// Walks the pixel's four bins (it is corner k of cell (y-dy, x-dx)), gathers the grad_out row of every entry
+// and accumulates in 64-bit fixed point in registers.  Pixels are taken from the coarsest level down: a
+// coarse pixel owns hundreds of entries, a fine one a handful, and the long items must not start last.
+// (Measured alternatives, all slower at cfg 2: one warp per pixel with interleaved entries, a flattened
+// 4-deep software pipeline over the four bins, and a magic-number replacement of the 64-bit F2I -- the
+// kernel is bound by its instruction count, ~45 per entry, not by the conversion or by load latency.)
+template <int D, typename VT>
+__global__ void __launch_bounds__(256)
+det_gather_kernel(const VT* __restrict__ grad_out, const int4* __restrict__ entries, const int* __restrict__ bin_start,
+                  const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
+                  const DetScale* __restrict__ det, VT* __restrict__ grad_value, int B, int S, int H, int L) {
+  constexpr int LANES = D / 4;
+  constexpr int RPC = 256 / LANES;
+  __shared__ CellTab tab;
+  load_cell_tab(&tab, shapes, lsi, L);
+  const int sub = (threadIdx.x & 31) % LANES;
+  const int64_t item = (int64_t)blockIdx.x * RPC + threadIdx.x / LANES;   // (b, reversed s, h), h fastest
+  if (item >= (int64_t)B * S * H) return;
+  const int h = (int)(item % H);
+  const int64_t bs = item / H;
+  const int s = S - 1 - (int)(bs % S);
+  const int64_t b = bs / S;
+  int l = 0;
+  for (int k = 1; k < L; ++k)
+    if (s >= tab.start[k]) l = k;
+  const int Wl = tab.W[l];
+  const int local = s - tab.start[l];
+  const int y = local / Wl, x = local - y * Wl;
+  const float scale = det->scale;
+  const int64_t bin0 = (b * H + h) * (int64_t)tab.cells_per_bh + tab.cell_begin[l];
+  long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (y < tab.H[l]) {   // guards a malformed pyramid (sum of level sizes < S)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int dy = k >> 1, dx = k & 1;   // this pixel is corner k (v1..v4 of cuh:56-80) of cell (y-dy, x-dx)
+      const int64_t bin = bin0 + (y - dy + 1) * (Wl + 1) + (x - dx + 1);
+      const int e0 = __ldg(bin_start + bin), e1 = __ldg(bin_start + bin + 1);
+      for (int e = e0; e < e1; ++e) {
+        const int4 ent = __ldg(entries + e);
+        const float lw = __int_as_float(ent.y), lh = __int_as_float(ent.z), aw = __int_as_float(ent.w);
+        const float hh = 1.0f - lh, hw = 1.0f - lw;
+        const float c = (k == 0 ? hh * hw : (k == 1 ? hh * lw : (k == 2 ? lh * hw : lh * lw))) * aw;
+        const float4 go = ld4(grad_out + (int64_t)ent.x * D + sub * 4);
+        a0 += __float2ll_rn((c * go.x) * scale);
+        a1 += __float2ll_rn((c * go.y) * scale);
+        a2 += __float2ll_rn((c * go.z) * scale);
+        a3 += __float2ll_rn((c * go.w) * scale);
+      }
+    }
+  }
+  const double inv = (double)det->inv_scale;
+  const float4 r = make_float4((float)((double)a0 * inv), (float)((double)a1 * inv), (float)((double)a2 * inv),
+                               (float)((double)a3 * inv));
+  st4(grad_value + ((b * S + s) * H + h) * (int64_t)D + sub * 4, r);
+}
+
+}  // namespace msda

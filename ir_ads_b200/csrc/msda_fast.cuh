@@ -523,6 +523,12 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 //
 // grad_value accumulation: float (vector red, fast, order-dependent rounding) or, for
 // MSDA_FLAG_DETERMINISTIC, 64-bit fixed point (integer red: the sum is order independent).
+// ACC = NoScatter compiles the grad_value scatter out (the sorted deterministic path computes grad_value
+// elsewhere, msda_det.cuh, and only needs this kernel's grad_sampling_loc / grad_attn_weight).
+struct NoScatter {
+  char unused;
+};
+
 __device__ __forceinline__ void scatter4(float* g, const float c, const float4 go, float /*scale*/) {
   // red (no return value) on purpose: atomicAdd(float4*) may compile to ATOM.E.ADD.F32x4 with a dead
   // destination, which pays the return trip; inline PTX pins SASS REDG.E.ADD.F32x4.
@@ -694,6 +700,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     }
 
     constexpr bool DET = sizeof(ACC) == 8;
+    constexpr bool SCATTER = sizeof(ACC) != sizeof(NoScatter);
     const int64_t img = (int64_t)cur.b * S * HD + sub * 4;
     const VT* vimg = value + img;
     ACC* gimg = grad_value + (DET ? img - sub * 3 : img);   // DET: lane offset is `sub`, not 4*sub
@@ -732,7 +739,9 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 #ifdef MSDA_EXP_NO_RED      // experiment builds only: what does the gather cost alone?
           if (cw.x == 12345.678f) scatter4(reinterpret_cast<float*>(gimg) + o00, cw.x, go_s, gscale);
 #else
-          if constexpr (DET) {
+          if constexpr (!SCATTER) {
+            (void)gscale;
+          } else if constexpr (DET) {
             if (cw.x != 0.0f) scatter4_det<LANES>(gimg + o00, cw.x, go_s, gscale);
             if (cw.y != 0.0f) scatter4_det<LANES>(gimg + o01, cw.y, go_s, gscale);
             if (cw.z != 0.0f) scatter4_det<LANES>(gimg + o10, cw.z, go_s, gscale);

@@ -48,7 +48,11 @@ def test_argument_errors_are_returned_not_printed():
     assert h.msda_forward(None, None, None, None, None, None, 0, 5, 8, 32, 4, 7, 4, None, 0, 0) == 0
     assert h.msda_backward_workspace_bytes(2, 10, 8, 32, 4, 3, 4, _lib.MSDA_BF16, 0) == 2 * 10 * 8 * 32 * 4
     assert h.msda_backward_workspace_bytes(2, 10, 8, 32, 4, 3, 4, _lib.MSDA_F32, 0) == 0
-    assert h.msda_backward_workspace_bytes(2, 10, 8, 32, 4, 3, 4, _lib.MSDA_F32, _lib.FLAG_DETERMINISTIC) == 2 * 10 * 8 * 32 * 8 + 64
+    # deterministic: fixed-point accumulators on generic shapes, bins + entries of the sorted path on fast shapes
+    assert h.msda_backward_workspace_bytes(2, 10, 8, 30, 4, 3, 4, _lib.MSDA_F32, _lib.FLAG_DETERMINISTIC) == 2 * 10 * 8 * 30 * 8 + 64
+    det = _lib.FLAG_DETERMINISTIC
+    assert h.msda_backward_workspace_bytes(2, 10, 8, 32, 4, 3, 4, _lib.MSDA_F32, det | _lib.FLAG_DET_ATOMIC) == 2 * 10 * 8 * 32 * 8 + 64
+    assert h.msda_backward_workspace_bytes(2, 10, 8, 32, 4, 3, 4, _lib.MSDA_F32, det) >= 2 * 3 * 8 * 4 * 4 * 16
 
 
 def test_product_never_imports_the_oracle():

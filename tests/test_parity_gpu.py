@@ -204,11 +204,33 @@ def test_deterministic_backward_is_bit_reproducible(dtype, D):
             assert np.array_equal(a, b)
     fast = run_cuda(value, shapes, lsi, loc, w, go, dtype)
     assert np.array_equal(fast[2], runs[0][2]) and np.array_equal(fast[3], runs[0][3])
+    # the sorted segment reduction (fast shapes) and the fixed-point reds give the same bits
+    atomic = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_DETERMINISTIC | _lib.FLAG_DET_ATOMIC)
+    for a, b in zip(runs[0], atomic):
+        assert np.array_equal(a, b)
     v64 = value.double().numpy()
     rgv, _, _ = msda_c.backward(go.double().numpy(), v64, shapes.numpy(), lsi.numpy(), loc.numpy(), w.numpy(), np.float64)
     tol = {torch.float32: 1e-5, torch.bfloat16: 1e-2, torch.float64: 1e-9}[dtype]
     assert_close(runs[0][1], rgv, tol, 1e-6, "deterministic grad_value vs oracle")
     assert_close(fast[1], rgv, tol, 1e-6, "atomic grad_value vs oracle")
+
+
+@pytest.mark.parametrize("cfg", ["enc", "dec"])
+def test_deterministic_sorted_path_on_pyramids(cfg):
+    """Sorted path on multi-level pyramids (encoder and decoder forms, edge locations included): bit-equal to
+    the fixed-point red path, reproducible, and within tolerance of the oracle."""
+    _, _lib, _, workloads, msda_c, _ = _mods()
+    levels = [(21, 37), (11, 19), (6, 10), (3, 5)]
+    kind, Q, dist = ("encoder", 0, "model") if cfg == "enc" else ("decoder", 333, "edge")
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, Q, 8, 32, 4, kind, dist, 17)
+    go = torch.randn(2, loc.shape[1], 256, generator=torch.Generator().manual_seed(5))
+    a = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_DETERMINISTIC)
+    b = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_DETERMINISTIC)
+    c = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_DETERMINISTIC | _lib.FLAG_DET_ATOMIC)
+    for x, y, z in zip(a, b, c):
+        assert np.array_equal(x, y) and np.array_equal(x, z)
+    rgv, _, _ = msda_c.backward(go.numpy(), value.numpy(), shapes.numpy(), lsi.numpy(), loc.numpy(), w.numpy(), np.float64)
+    assert_close(a[1], rgv, 1e-5, 1e-6, "sorted deterministic grad_value vs oracle")
 
 
 def test_deterministic_backward_scale_extremes():
