@@ -134,3 +134,37 @@ class DeformableEncoder(nn.Module):
         if self.post_norm_layer is not None:
             query = self.post_norm_layer(query)
         return query
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder side: what DINOTransformerDecoder feeds the cross-attention op
+# ------------------------------------------------------------------------------------------------
+def decoder_reference_points_input(reference_points: torch.Tensor, valid_ratios: torch.Tensor) -> torch.Tensor:
+    """Per-level reference boxes / points for the decoder's MSDeformAttn cross-attention
+    (dino_transformer.py:186-194): ``[B, Q, 4]`` boxes are scaled by ``cat(valid_ratios, valid_ratios)``,
+    ``[B, Q, 2]`` points by ``valid_ratios``; result ``[B, Q, L, 4 | 2]`` -- the module's ``reference_points``."""
+    if reference_points.shape[-1] == 4:
+        return reference_points[:, :, None] * torch.cat([valid_ratios, valid_ratios], -1)[:, None]
+    if reference_points.shape[-1] == 2:
+        return reference_points[:, :, None] * valid_ratios[:, None]
+    raise ValueError(f"reference_points last dim must be 2 or 4, got {reference_points.shape[-1]}")
+
+
+class DeformableCrossAttentionBlock(nn.Module):
+    """The MSDeformAttn cross-attention + norm step of a DINO decoder layer (``cross_attn`` then ``norm`` in
+    the layer's operation order, dino_transformer.py:124-150): queries attend to the encoder memory through
+    per-level reference boxes.  The decoder's self-attention (nn.MultiheadAttention) and FFN stay PyTorch."""
+
+    def __init__(self, embed_dim=256, num_heads=8, attn_dropout=0.1, num_feature_levels=4, num_points=4):
+        super().__init__()
+        self.attn = MultiScaleDeformableAttention(embed_dim=embed_dim, num_heads=num_heads,
+                                                  num_levels=num_feature_levels, num_points=num_points,
+                                                  dropout=attn_dropout, batch_first=True)
+        self.norm = nn.LayerNorm(embed_dim)
+
+    def forward(self, query, memory, query_pos, reference_points, valid_ratios, spatial_shapes, level_start_index,
+                key_padding_mask=None):
+        ref_in = decoder_reference_points_input(reference_points, valid_ratios)
+        out = self.attn(query, None, memory, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
+                        reference_points=ref_in, spatial_shapes=spatial_shapes, level_start_index=level_start_index)
+        return self.norm(out)

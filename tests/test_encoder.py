@@ -96,3 +96,52 @@ def test_encoder_stack_matches_fp64_cpu_restatement():
     got = run(enc.float().to(dev), dev, torch.float32, None)
     err = (got.detach().cpu().double() - want).abs().max().item()
     assert err <= 5e-5 * want.abs().max().item() + 1e-5, err
+
+
+def test_decoder_reference_points_input():
+    ref4 = torch.tensor([[[0.5, 0.5, 0.2, 0.4]]])
+    vr = torch.tensor([[[1.0, 1.0], [0.5, 0.25]]])
+    out = encoder.decoder_reference_points_input(ref4, vr)
+    assert out.shape == (1, 1, 2, 4)
+    assert torch.allclose(out[0, 0, 1], torch.tensor([0.25, 0.125, 0.1, 0.1]))
+    out2 = encoder.decoder_reference_points_input(ref4[..., :2], vr)
+    assert torch.allclose(out2[0, 0, 1], torch.tensor([0.25, 0.125]))
+    with pytest.raises(ValueError):
+        encoder.decoder_reference_points_input(torch.zeros(1, 1, 3), vr)
+
+
+@pytest.mark.gpu
+def test_decoder_cross_attention_block_matches_fp64_restatement():
+    from oracle import msda_torch
+    torch.manual_seed(2)
+    dev = "cuda:0"
+    levels = [(9, 12), (5, 6), (3, 3)]
+    B, Q, C = 2, 17, 64
+    S = sum(h * w for h, w in levels)
+    blk = encoder.DeformableCrossAttentionBlock(embed_dim=C, num_heads=4, attn_dropout=0.0, num_feature_levels=3,
+                                                num_points=2)
+    with torch.no_grad():
+        blk.attn.sampling_offsets.weight.normal_(0, 0.05)
+        blk.attn.attention_weights.weight.normal_(0, 0.2)
+    q, mem, pos = torch.randn(B, Q, C), torch.randn(B, S, C), torch.randn(B, Q, C) * 0.1
+    ref = torch.rand(B, Q, 4) * torch.tensor([1, 1, 0.4, 0.4]) + torch.tensor([0, 0, 0.05, 0.05])
+    vr = torch.rand(B, 3, 2) * 0.3 + 0.7
+    mask = torch.zeros(B, S, dtype=torch.bool)
+    mask[1, -4:] = True
+    from ir_ads_b200.workloads import level_tensors
+    ss, lsi = level_tensors(levels, "cpu")
+    # float64 restatement around the oracle op
+    d = blk.double()
+    a = d.attn
+    H, L, P = 4, 3, 2
+    refin = encoder.decoder_reference_points_input(ref.double(), vr.double())
+    qq = q.double() + pos.double()
+    v = a.value_proj(mem.double()).masked_fill(mask[..., None], 0.0).view(B, S, H, -1)
+    off = a.sampling_offsets(qq).view(B, Q, H, L, P, 2)
+    w = a.attention_weights(qq).view(B, Q, H, L * P).softmax(-1).view(B, Q, H, L, P)
+    loc = refin[:, :, None, :, None, :2] + off / P * refin[:, :, None, :, None, 2:] * 0.5
+    want = d.norm(a.output_proj(msda_torch.forward(v, levels, loc, w)) + q.double()).detach()
+    blk = blk.float().to(dev)
+    got = blk(q.to(dev), mem.to(dev), pos.to(dev), ref.to(dev), vr.to(dev), ss.to(dev), lsi.to(dev), mask.to(dev))
+    err = (got.detach().cpu().double() - want).abs().max().item()
+    assert err <= 5e-5 * want.abs().max().item() + 1e-5, err

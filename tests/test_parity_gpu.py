@@ -270,7 +270,8 @@ def test_bookkeeping_bit_exact(dist):
 # against the reference's own CUDA kernels built for sm_100a (oracle/_ref)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cfg,batch,dist", [("cfg1", 2, "model"), ("cfg1", 2, "edge"), ("cfg2", 2, "model"),
-                                            ("cfg2", 1, "test"), ("cfg3_f32", 8, "model")])
+                                            ("cfg2", 1, "test"), ("cfg3_f32", 8, "model"), ("cfg4", 2, "model"),
+                                            ("cfg5", 1, "model")])
 def test_against_reference_cuda_kernels(cfg, batch, dist):
     """Whole-tensor comparison with the reference's own kernels (compiled unmodified for sm_100a) at the
     BASELINE shapes, including the full encoder shape the CPU oracle cannot reach."""
@@ -281,7 +282,11 @@ def test_against_reference_cuda_kernels(cfg, batch, dist):
     wl = workloads.WORKLOADS[cfg]
     value, shapes, lsi, loc, w = workloads.make_workload_inputs(wl, dist, 5, DEV, batch=batch)
     go = torch.randn(batch, wl.queries, 256, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6))
-    out, gv, gl, gw = run_cuda(value, shapes, lsi, loc, w, go)
+    flags = _mods()[1].FLAG_DETERMINISTIC if wl.deterministic else 0      # cfg 5 asks for the deterministic backward
+    out, gv, gl, gw = run_cuda(value, shapes, lsi, loc, w, go, flags=flags)
+    if wl.deterministic:
+        again = run_cuda(value, shapes, lsi, loc, w, go, flags=flags)
+        assert all(np.array_equal(a, b) for a, b in zip((out, gv, gl, gw), again))
     f = lambda t: t.double().cpu().numpy()
     # yardstick: the reference kernels evaluated in float64 on the same float32 inputs
     truth = [f(t) for t in ref_cuda.forward_backward(value.double(), shapes, lsi, loc.double(), w.double(), go.double())]
