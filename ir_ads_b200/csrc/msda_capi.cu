@@ -130,7 +130,7 @@ bool use_tiled(const Dims& d, unsigned flags) {
   if (!(d.Q == d.S && (flags & MSDA_FLAG_ORDER_TILED) && !(flags & MSDA_FLAG_ORDER_LINEAR))) return false;
   // the persistent 1024-thread CTAs stage records + raw loc/w for 4096/D rows; the row order is only a
   // scheduling choice, so fall back to the default order when that does not fit in shared memory
-  const int NP = d.L * d.P, rpc = 1024 / (d.D / 4);
+  const int NP = d.L * d.P, rpc = 1024 / (d.D / 8 > 0 ? d.D / 8 : 1);   // worst case: 8 channels per lane
   const size_t words = (size_t)rpc * (size_t)(msda::bwd_row_words(NP, true) > msda::fwd_row_words(NP, true)
                                                   ? msda::bwd_row_words(NP, true)
                                                   : msda::fwd_row_words(NP, true));
@@ -148,13 +148,18 @@ bool use_tile2d(const Dims& d, unsigned flags) {
 // slack covers them, the kernel's grid-stride step covers anything else.
 int64_t tile2d_bound(const Dims& d, int rpc) { return ((int64_t)d.S + rpc - 1) / rpc * 5 / 4 + 32 * (int64_t)d.L; }
 
+// channels per lane: 8 for bf16 rows of 32+ channels (16-byte lane loads), else 4
+template <int D, typename VT>
+constexpr int cpl_of() { return (sizeof(VT) == 2 && D >= 32) ? 8 : 4; }
+
 template <int D, typename VT, int PT, int THREADS, int TILED, int PRE = 0>
 int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
                     const void* loc, const void* w, void* out, msda::FusedArgs fa = msda::FusedArgs{}) {
-  using G = msda::Geom<D, THREADS>;
+  constexpr int CPL = cpl_of<D, VT>();
+  using G = msda::Geom<D * 4 / CPL, THREADS>;
   const int NP = d.L * d.P;
   const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::fwd_row_words(NP, TILED == 1) * 4;
-  auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED, PRE>;
+  auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED, PRE, CPL>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
@@ -172,10 +177,14 @@ template <int D, typename VT, int PT, int THREADS, int TILED, typename ACC, int 
 int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
                     const int64_t* lsi, const void* loc, const void* w, ACC* gv, void* gl, void* gw,
                     const msda::DetScale* det, msda::FusedArgs fa = msda::FusedArgs{}) {
-  using G = msda::Geom<D, THREADS>;
+  // The backward keeps 4 channels per lane for every type: it is bound by the grad_value reds, and those run
+  // fastest as one full 128-byte line per row and instruction (8 channels per lane -> two 64-byte halves per
+  // row: 1.75 -> 2.09 ms at cfg2 with bf16 value), so the faster 16-byte gather buys nothing there.
+  constexpr int CPL = 4;
+  using G = msda::Geom<D * 4 / CPL, THREADS>;
   const int NP = d.L * d.P;
   const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::bwd_row_words(NP, TILED == 1) * 4;
-  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC, PRE>;
+  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC, PRE, CPL>;
   MSDA_CUDA(ensure_smem(k, smem));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);

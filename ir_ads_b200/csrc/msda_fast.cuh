@@ -66,6 +66,75 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b) {
   return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
 }
 
+// ---- CPL-channel lane vectors: 4 channels per lane (one 16-byte float load, or 8 bytes of bf16), or 8 bf16
+// channels per lane (one 16-byte load).  The L1 data path is limited per 16-byte lane access, not per byte
+// (profiles/r01m_microbench_ceilings.txt, item 5), so bf16 rows are gathered with 8 channels per lane.
+template <int N>
+struct Vec {
+  float v[N];
+};
+template <int N>
+__device__ __forceinline__ Vec<N> vzero() {
+  Vec<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.v[i] = 0.0f;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Vec<N> ldv(const float* p) {
+  static_assert(N == 4, "float rows use 4 channels per lane");
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  Vec<4> r;
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Vec<N> ldv(const __nv_bfloat16* p) {
+  Vec<N> r;
+  if constexpr (N == 4) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    r.v[0] = __uint_as_float(u.x << 16); r.v[1] = __uint_as_float(u.x & 0xffff0000u);
+    r.v[2] = __uint_as_float(u.y << 16); r.v[3] = __uint_as_float(u.y & 0xffff0000u);
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    r.v[0] = __uint_as_float(u.x << 16); r.v[1] = __uint_as_float(u.x & 0xffff0000u);
+    r.v[2] = __uint_as_float(u.y << 16); r.v[3] = __uint_as_float(u.y & 0xffff0000u);
+    r.v[4] = __uint_as_float(u.z << 16); r.v[5] = __uint_as_float(u.z & 0xffff0000u);
+    r.v[6] = __uint_as_float(u.w << 16); r.v[7] = __uint_as_float(u.w & 0xffff0000u);
+  }
+  return r;
+}
+template <int N>
+__device__ __forceinline__ void stv(float* p, const Vec<N>& a) {
+  static_assert(N == 4, "float rows use 4 channels per lane");
+  *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const unsigned*>(&t);
+}
+template <int N>
+__device__ __forceinline__ void stv(__nv_bfloat16* p, const Vec<N>& a) {
+  if constexpr (N == 4) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a.v[0], a.v[1]), pack_bf16x2(a.v[2], a.v[3]));
+  } else {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(a.v[0], a.v[1]), pack_bf16x2(a.v[2], a.v[3]),
+                                              pack_bf16x2(a.v[4], a.v[5]), pack_bf16x2(a.v[6], a.v[7]));
+  }
+}
+template <int N>
+__device__ __forceinline__ void fmav(Vec<N>& acc, const float s, const Vec<N>& x) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc.v[i] = fmaf(s, x.v[i], acc.v[i]);
+}
+template <int N>
+__device__ __forceinline__ float dotv(const Vec<N>& a, const Vec<N>& b) {
+  float r = a.v[0] * b.v[0];
+#pragma unroll
+  for (int i = 1; i < N; ++i) r = fmaf(a.v[i], b.v[i], r);
+  return r;
+}
+
 // ---- level / tile table in shared memory -----------------------------------------------------
 struct LevelTab {
   int H[kFastMaxLevels];
@@ -393,7 +462,7 @@ __device__ __forceinline__ float row_softmax(const float* logits_row, float* scr
 // TILED (persistent): software pipeline per warp -- wait for this item's raw loc/w in shared memory
 //   -> phase 1: records -> issue cp.async for the NEXT item's loc/w -> phase 2: gather (the long
 //   phase, hides the HBM latency of the copy).
-template <int D, typename VT, int PT, int THREADS, int ORDER, int PRE>
+template <int D, typename VT, int PT, int THREADS, int ORDER, int PRE, int CPL>
 #ifndef MSDA_FWD_MINB
 #define MSDA_FWD_MINB 6
 #endif
@@ -403,7 +472,8 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
                      const float* __restrict__ w, VT* __restrict__ out, const FusedArgs fused, int B, int S, int H,
                      int L, int Q, int P, int64_t rows) {
   // FUSED: `loc` holds raw sampling offsets and `w` attention logits (see FusedArgs)
-  using G = Geom<D, THREADS>;
+  constexpr int DL = D * 4 / CPL;               // lane geometry: LANES = D / CPL lanes per row
+  using G = Geom<DL, THREADS>;
   constexpr int LANES = G::LANES;
   constexpr bool STAGED = (ORDER == 1);
   constexpr bool FUSED = (PRE == kPreFused);
@@ -427,7 +497,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   float2* raw_xy = reinterpret_cast<float2*>(my + ((5 * NP + 1) & ~1));
   float* raw_w = my + ((5 * NP + 1) & ~1) + 2 * NP;
 
-  RowWalk<D, THREADS, ORDER> walk(tab, B, H, rows);
+  RowWalk<DL, THREADS, ORDER> walk(tab, B, H, rows);
   if (walk.done()) return;
   RowRef cur = walk.get(tab, L, H, Q);
   if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
@@ -477,9 +547,9 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 
     // ---- phase 2: gather ----
     if (cur.live) {
-      const VT* vimg = value + (int64_t)cur.b * S * HD + sub * 4;
+      const VT* vimg = value + (int64_t)cur.b * S * HD + sub * CPL;
       asm volatile("" : "+l"(vimg));   // keep the row base as ONE 64-bit register: corner address = base + off*4 (IMAD.WIDE)
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      Vec<CPL> acc = vzero<CPL>();
       int pt = 0;
       for (int l = 0; l < L; ++l) {
         const int dyl = tab->W[l] * HD;
@@ -491,17 +561,17 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
           const int o00 = oc & ~15;
           const int o01 = o00 + ((oc & 1) ? HD : 0);
           const int dy = (oc & 2) ? dyl : 0;
-          const float4 v00 = ld4(vimg + o00);
-          const float4 v01 = ld4(vimg + o01);
-          const float4 v10 = ld4(vimg + (o00 + dy));
-          const float4 v11 = ld4(vimg + (o01 + dy));
-          fma4(acc, cw.x, v00);
-          fma4(acc, cw.y, v01);
-          fma4(acc, cw.z, v10);
-          fma4(acc, cw.w, v11);
+          const Vec<CPL> v00 = ldv<CPL>(vimg + o00);
+          const Vec<CPL> v01 = ldv<CPL>(vimg + o01);
+          const Vec<CPL> v10 = ldv<CPL>(vimg + (o00 + dy));
+          const Vec<CPL> v11 = ldv<CPL>(vimg + (o01 + dy));
+          fmav(acc, cw.x, v00);
+          fmav(acc, cw.y, v01);
+          fmav(acc, cw.z, v10);
+          fmav(acc, cw.w, v11);
         }
       }
-      st4(out + cur.row * D + sub * 4, acc);
+      stv<CPL>(out + cur.row * D + sub * CPL, acc);
     }
     if constexpr (STAGED) {
       if (!has_next) break;
@@ -536,6 +606,36 @@ __device__ __forceinline__ void scatter4(float* g, const float c, const float4 g
                "f"(c * go.w)
                : "memory");
 }
+// `go` is in SCATTER layout: component block i (4 floats) belongs to channels i*HALF + 4*sub .. +3, and `g`
+// already points at channel 4*sub, so the LANES lanes of a row write 16*LANES CONTIGUOUS bytes per instruction
+// (with 8 channels per lane the gather layout would put two separate 16-byte reds into every 32-byte
+// sector and double the L2 reduction work: measured 1.75 -> 2.9 ms).
+template <int N, int HALF>
+__device__ __forceinline__ void scatterv(float* g, const float c, const Vec<N>& go) {
+#pragma unroll
+  for (int i = 0; i < N; i += 4)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + (i / 4) * HALF), "f"(c * go.v[i]),
+                 "f"(c * go.v[i + 1]), "f"(c * go.v[i + 2]), "f"(c * go.v[i + 3])
+                 : "memory");
+}
+
+// grad_out row in scatter layout (see scatterv): for 4 channels per lane it is the gather layout itself
+template <int N, int D, typename VT>
+__device__ __forceinline__ Vec<N> load_scatter_layout(const VT* row, int sub, const Vec<N>& gather_layout) {
+  if constexpr (N == 4) {
+    return gather_layout;
+  } else {
+    const Vec<4> a = ldv<4>(row + sub * 4), b = ldv<4>(row + D / 2 + sub * 4);
+    Vec<8> r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[i] = a.v[i];
+      r.v[4 + i] = b.v[i];
+    }
+    return r;
+  }
+}
+
 // Deterministic flavour: `go` holds the TRANSPOSED channels (component i = channel i*LANES + sub, see
 // transpose_channels), and g already points at channel `sub`, so the LANES lanes of a row write 8*LANES
 // contiguous bytes per instruction: every 32-byte sector receives one full-width 64-bit red per lane
@@ -602,7 +702,7 @@ __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
 #ifndef MSDA_BWD_MINB
 #define MSDA_BWD_MINB 4
 #endif
-template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC, int PRE>
+template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC, int PRE, int CPL>
 __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_BWD_MINB : 1)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
@@ -611,7 +711,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                      float* __restrict__ grad_w, const DetScale* __restrict__ det, const FusedArgs fused, int B,
                      int S, int H, int L, int Q, int P, int64_t rows) {
   // FUSED: loc = raw offsets, w = logits in; grad_loc = grad of the offsets, grad_w = grad of the logits out
-  using G = Geom<D, THREADS>;
+  constexpr int DL = D * 4 / CPL;
+  using G = Geom<DL, THREADS>;
   constexpr int LANES = G::LANES;
   constexpr bool STAGED = (ORDER == 1);
   constexpr bool FUSED = (PRE == kPreFused);
@@ -639,12 +740,12 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 
   // A warp stays converged for the full-mask shuffles below: rows that do not exist (edge tiles,
   // the tail of the last CTA) get all-zero weights, so they scatter nothing and never write.
-  RowWalk<D, THREADS, ORDER> walk(tab, B, H, rows);
+  RowWalk<DL, THREADS, ORDER> walk(tab, B, H, rows);
   if (walk.done()) return;
   RowRef cur = walk.get(tab, L, H, Q);
   if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
-  float4 go = zero;
-  if (STAGED && cur.live) go = ld4(grad_out + cur.row * D + sub * 4);
+  Vec<CPL> go = vzero<CPL>();
+  if (STAGED && cur.live) go = ldv<CPL>(grad_out + cur.row * D + sub * CPL);
   while (true) {
     bool has_next = false;
     RowRef nxt = cur;
@@ -655,7 +756,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
       cp_async_wait_all();
       __syncwarp();
     } else {
-      go = cur.live ? ld4(grad_out + cur.row * D + sub * 4) : zero;
+      go = cur.live ? ldv<CPL>(grad_out + cur.row * D + sub * CPL) : vzero<CPL>();
     }
     const float* rp = FUSED ? fused.ref + (cur.row / H) * (int64_t)L * fused.ref_dim : nullptr;
     {
@@ -691,22 +792,31 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
       }
     }
     __syncwarp();
-    float4 go_next = zero;
+    Vec<CPL> go_next = vzero<CPL>();
     if constexpr (STAGED) {
       if (has_next) {
         stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
-        if (nxt.live) go_next = ld4(grad_out + nxt.row * D + sub * 4);
+        if (nxt.live) go_next = ldv<CPL>(grad_out + nxt.row * D + sub * CPL);
       }
     }
 
     constexpr bool DET = sizeof(ACC) == 8;
     constexpr bool SCATTER = sizeof(ACC) != sizeof(NoScatter);
-    const int64_t img = (int64_t)cur.b * S * HD + sub * 4;
+    static_assert(!(sizeof(ACC) == 8 && CPL != 4), "the fixed-point red path transposes 4 channels per lane");
+    const int64_t img = (int64_t)cur.b * S * HD + sub * CPL;
     const VT* vimg = value + img;
     ACC* gimg = grad_value + (DET ? img - sub * 3 : img);   // DET: lane offset is `sub`, not 4*sub
     asm volatile("" : "+l"(vimg), "+l"(gimg));
-    float4 go_s = go;                                        // what the scatter multiplies
-    if constexpr (DET) go_s = transpose_channels<LANES>(go, sub);   // one 64-bit register each: address = base + off*size (IMAD.WIDE)
+    float4 go_s = make_float4(0.f, 0.f, 0.f, 0.f);           // DET only: channels transposed across the lanes
+    if constexpr (DET) go_s = transpose_channels<LANES>(make_float4(go.v[0], go.v[1], go.v[2], go.v[3]), sub);
+    // float scatter: grad_out in scatter layout, base pointer at channel 4*sub (== the gather base for CPL 4)
+    Vec<CPL> go_sc = go;
+    float* gsc = nullptr;
+    if constexpr (SCATTER && !DET) {
+      go_sc = load_scatter_layout<CPL, D>(grad_out + cur.row * D, sub, go);
+      gsc = reinterpret_cast<float*>(grad_value) + (int64_t)cur.b * S * HD + sub * 4;
+      asm volatile("" : "+l"(gsc));
+    }   // one 64-bit register each: address = base + off*size (IMAD.WIDE)
     float* glp = grad_loc + cur.row * (int64_t)NP * 2;
     float* gwp = grad_w + cur.row * (int64_t)NP;
 
@@ -725,19 +835,19 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           const int dy = (oc & 2) ? tab->W[l] * HD : 0;
           const int o10 = o00 + dy, o11 = o01 + dy;
 #ifdef MSDA_EXP_NO_GATHER   // experiment builds only (tools/ablate.sh): what does the scatter cost alone?
-          const float4 v00 = cw, v01 = cw, v10 = cw, v11 = cw;
+          const Vec<CPL> v00 = go, v01 = go, v10 = go, v11 = go;
 #else
-          const float4 v00 = ld4(vimg + o00);
-          const float4 v01 = ld4(vimg + o01);
-          const float4 v10 = ld4(vimg + o10);
-          const float4 v11 = ld4(vimg + o11);
+          const Vec<CPL> v00 = ldv<CPL>(vimg + o00);
+          const Vec<CPL> v01 = ldv<CPL>(vimg + o01);
+          const Vec<CPL> v10 = ldv<CPL>(vimg + o10);
+          const Vec<CPL> v11 = ldv<CPL>(vimg + o11);
 #endif
-          d[4 * j + 0] = dot4(go, v00);
-          d[4 * j + 1] = dot4(go, v01);
-          d[4 * j + 2] = dot4(go, v10);
-          d[4 * j + 3] = dot4(go, v11);
+          d[4 * j + 0] = dotv(go, v00);
+          d[4 * j + 1] = dotv(go, v01);
+          d[4 * j + 2] = dotv(go, v10);
+          d[4 * j + 3] = dotv(go, v11);
 #ifdef MSDA_EXP_NO_RED      // experiment builds only: what does the gather cost alone?
-          if (cw.x == 12345.678f) scatter4(reinterpret_cast<float*>(gimg) + o00, cw.x, go_s, gscale);
+          if (cw.x == 12345.678f) scatterv<CPL, D / 2>(reinterpret_cast<float*>(gimg) + o00, cw.x, go);
 #else
           if constexpr (!SCATTER) {
             (void)gscale;
@@ -747,10 +857,10 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             if (cw.z != 0.0f) scatter4_det<LANES>(gimg + o10, cw.z, go_s, gscale);
             if (cw.w != 0.0f) scatter4_det<LANES>(gimg + o11, cw.w, go_s, gscale);
           } else {
-            if (cw.x != 0.0f) scatter4(gimg + o00, cw.x, go_s, gscale);
-            if (cw.y != 0.0f) scatter4(gimg + o01, cw.y, go_s, gscale);
-            if (cw.z != 0.0f) scatter4(gimg + o10, cw.z, go_s, gscale);
-            if (cw.w != 0.0f) scatter4(gimg + o11, cw.w, go_s, gscale);
+            if (cw.x != 0.0f) scatterv<CPL, D / 2>(gsc + o00, cw.x, go_sc);
+            if (cw.y != 0.0f) scatterv<CPL, D / 2>(gsc + o01, cw.y, go_sc);
+            if (cw.z != 0.0f) scatterv<CPL, D / 2>(gsc + o10, cw.z, go_sc);
+            if (cw.w != 0.0f) scatterv<CPL, D / 2>(gsc + o11, cw.w, go_sc);
           }
 #endif
         } else {
