@@ -7,9 +7,11 @@
 //   :56-80    each of the four corners is zero-padded individually
 //
 // Float path: the reference rounds loc*size to fp32 before it subtracts 0.5, which costs up to
-// ~4e-6 px at size ~170 and occasionally picks the neighbouring cell.  Here the rounding error of
-// the product is recovered with one fma (e = fma(loc,size,-p) is exact), so cell and fraction are
-// those of the EXACT value of loc*size-0.5 -- the same cell the fp64 grid_sample oracle picks.
+// ~4e-6 px at size ~170 and occasionally picks the neighbouring cell.  Here the rounding errors of
+// the product (one fma: e = fma(loc,size,-p) is exact) and of the subtraction (TwoSum) are carried
+// along, so cell + fraction equal the EXACT value of loc*size-0.5 to the last float bit of the
+// fraction -- the same cell the fp64 grid_sample oracle picks (when the exact fraction rounds up to
+// 1.0 the result is (cell, 1.0), the same sample as (cell+1, 0)).
 // oracle/msda_oracle.c::split_f32_compensated restates these lines operation for operation; the
 // bookkeeping test compares the two bit for bit, so keep them in lock step.
 #pragma once
@@ -35,11 +37,12 @@ __device__ __forceinline__ AxisSplit<float> split_axis(float loc, int size) {
   AxisSplit<float> s;
   const float sz = (float)size;
   const float p = __fmul_rn(loc, sz);
-  const float e = __fmaf_rn(loc, sz, -p);
+  const float e = __fmaf_rn(loc, sz, -p);                 // loc*sz == p + e exactly
   const float a = __fsub_rn(p, 0.5f);
+  const float bb = __fsub_rn(a, p);                       // TwoSum: p - 0.5 == a + ea exactly
+  const float ea = __fadd_rn(__fsub_rn(p, __fsub_rn(a, bb)), __fsub_rn(-0.5f, bb));
   float f0 = floorf(a);
-  const float d = __fsub_rn(__fsub_rn(p, f0), 0.5f);
-  float r = __fadd_rn(d, e);
+  float r = __fadd_rn(__fsub_rn(a, f0), __fadd_rn(ea, e));   // a - floor(a) is exact whenever it is representable
   if (r < 0.0f) {
     f0 -= 1.0f;
     r = __fadd_rn(r, 1.0f);

@@ -76,14 +76,19 @@ static axis_t split_f32_reference(float loc, int size) {
 static axis_t split_f32_compensated(float loc, int size) {
   axis_t a;
   const float sz = (float)size;
-  volatile float p = loc * sz;    /* rounded product                         */
-  float e = fmaf(loc, sz, -p);    /* exact rounding error of the product     */
+  volatile float p = loc * sz;    /* rounded product                                  */
+  float e = fmaf(loc, sz, -p);    /* loc*sz == p + e exactly                          */
   volatile float av = p - 0.5f;
+  volatile float bb = av - p;     /* TwoSum: p - 0.5 == av + ea exactly               */
+  volatile float t1 = av - bb;
+  volatile float t2 = p - t1;
+  volatile float t3 = -0.5f - bb;
+  volatile float ea = t2 + t3;
   float f0 = floorf(av);
-  volatile float d0 = p - f0;
-  volatile float d = d0 - 0.5f;
-  volatile float r0 = d + e;
-  float r = r0;
+  volatile float r0 = av - f0;
+  volatile float tt = ea + e;
+  volatile float rr = r0 + tt;
+  float r = rr;
   if (r < 0.0f) { f0 -= 1.0f; volatile float t = r + 1.0f; r = t; }
   else if (r >= 1.0f) { f0 += 1.0f; volatile float t = r - 1.0f; r = t; }
   /* gate: exact coord = f0 + r, r in [0,1].  coord > -1  <=>  f0 >= 0 or (f0 == -1 and r > 0);
