@@ -88,6 +88,20 @@ extern "C" {
 #define MSDA_FLAG_ORDER_STRIP (1u << 4)
 /* Encoder form only (Q == S): one CTA = an 8x4-pixel tile (at D=32) of one level and ONE head, non-persistent. */
 #define MSDA_FLAG_ORDER_TILE2D (1u << 5)
+/* STRIP order: strips ordered (image, head, strip) instead of (image, strip, head), so that the CTAs resident on
+ * an SM work on the same head (A/B testing; measured no faster). */
+#define MSDA_FLAG_STRIP_HEAD_MAJOR (1u << 10)
+/* Backward (float accumulation, D in {32,64,128}), OPT-IN experiment: grad_value of the coarsest pyramid levels
+ * -- as many as fit in ~200 KB of shared memory, decided on the device from the level shapes -- is pre-aggregated
+ * on chip by a second, persistent kernel (one warp per level and pixel-parity class, no atomics;
+ * csrc/msda_coarse.cuh) instead of one vector red per sample, which halves the L2 reduction traffic at pyramid
+ * shapes.  With a host copy of the shapes (msda_backward_hs) the kernel runs concurrently with the main
+ * backward kernel on a library-owned side stream that forks from / joins `stream`; serially on `stream` while
+ * it is being graph-captured or without the host copy.  Same results up to float summation order.
+ * Measured slower than the default all-reds backward on B200, hence never the default. */
+#define MSDA_FLAG_COARSE_OFF (1u << 7)    /* never use it (wins over COARSE_ON)                            */
+#define MSDA_FLAG_COARSE_ON (1u << 8)     /* use it                                                        */
+#define MSDA_FLAG_COARSE_SERIAL (1u << 9) /* both kernels on `stream`, one after the other                */
 
 int msda_abi_version(void);
 
@@ -109,6 +123,19 @@ int msda_backward(void* stream, const void* grad_output, const void* value,
                   int num_heads, int channels, int num_levels, int num_query, int num_point,
                   void* grad_value, void* grad_sampling_loc, void* grad_attn_weight,
                   void* workspace, size_t workspace_bytes, int dtype, unsigned flags);
+
+/* msda_backward with an optional HOST copy of spatial_shapes ([L, 2] int64, may be NULL = msda_backward).
+ * The library never reads device memory on the host, so without the copy it cannot know the level sizes; with
+ * it, the shared-memory tile of the coarse-level accumulation (MSDA_FLAG_COARSE_*, below) is sized exactly and
+ * that kernel shares every SM with the main backward kernel.  The copy must equal the device tensor; it is
+ * only used to size launches, never for arithmetic (both kernels re-derive everything from the device shapes). */
+int msda_backward_hs(void* stream, const void* grad_output, const void* value,
+                     const int64_t* spatial_shapes, const int64_t* level_start_index,
+                     const void* sampling_loc, const void* attn_weight, int batch, int spatial_size,
+                     int num_heads, int channels, int num_levels, int num_query, int num_point,
+                     void* grad_value, void* grad_sampling_loc, void* grad_attn_weight,
+                     void* workspace, size_t workspace_bytes, int dtype, unsigned flags,
+                     const int64_t* spatial_shapes_host);
 
 /*
  * Fused module path (an extension, the reference has no counterpart): the

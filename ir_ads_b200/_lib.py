@@ -25,6 +25,10 @@ FLAG_ORDER_TILED = 1 << 3
 FLAG_ORDER_STRIP = 1 << 4
 FLAG_ORDER_TILE2D = 1 << 5
 FLAG_DET_ATOMIC = 1 << 6
+FLAG_COARSE_OFF = 1 << 7
+FLAG_COARSE_ON = 1 << 8
+FLAG_COARSE_SERIAL = 1 << 9
+FLAG_STRIP_HEAD_MAJOR = 1 << 10
 ABI_VERSION = 1
 
 _lock = threading.Lock()
@@ -57,6 +61,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_backward_workspace_bytes.argtypes = [i, i, i, i, i, i, i, i, u]
     lib.msda_backward.restype = i
     lib.msda_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, vp, vp, sz, i, u]
+    lib.msda_backward_hs.restype = i
+    lib.msda_backward_hs.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, vp, vp, sz, i, u, vp]
     lib.msda_fused_supported.restype = i
     lib.msda_fused_supported.argtypes = [i, i, i, i, i, i, u]
     lib.msda_fused_forward.restype = i

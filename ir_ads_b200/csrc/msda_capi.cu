@@ -13,11 +13,24 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "msda_fast.cuh"
 #include "msda_generic.cuh"
 #include "msda_det.cuh"
+
+namespace msda {
+// msda_coarse_launch.cu (kernel: msda_coarse.cuh)
+constexpr int kCoarseBatch = 32;
+constexpr int coarse_stage_bytes(int D, int elem_size, int L, int P) {
+  return kCoarseBatch * (D * elem_size + (L < kCoarseMaxLevels ? L : kCoarseMaxLevels) * P * 12);
+}
+cudaError_t launch_bwd_coarse(cudaStream_t st, bool value_is_bf16, const void* go, const int64_t* shapes,
+                              const int64_t* lsi, const float* loc, const float* w, float* gv, int B, int S, int H,
+                              int D, int L, int Q, int P, int budget);
+}  // namespace msda
 
 namespace {
 
@@ -66,6 +79,15 @@ struct DeviceGuard {
     if (switched) cudaSetDevice(prev);
   }
 };
+
+// Experiment knobs (tools/ only; results with MSDA_EXP_SKIP_COARSE_KERNEL are WRONG on purpose):
+//   MSDA_EXP_BWD_SMEM_PAD=<bytes>   extra dynamic shared memory per CTA of the main backward kernel (occupancy study)
+//   MSDA_EXP_BWD_CARVEOUT=<percent> preferred shared-memory carveout of the main backward kernel (L1 size study)
+//   MSDA_EXP_SKIP_COARSE_KERNEL=1   plan the coarse-level split but do not launch the coarse kernel (times the rest)
+int exp_env(const char* name) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : 0;
+}
 
 struct Dims {
   int B, S, H, D, L, Q, P;
@@ -154,7 +176,8 @@ constexpr int cpl_of() { return (sizeof(VT) == 2 && D >= 32) ? 8 : 4; }
 
 template <int D, typename VT, int PT, int THREADS, int TILED, int PRE = 0>
 int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
-                    const void* loc, const void* w, void* out, msda::FusedArgs fa = msda::FusedArgs{}) {
+                    const void* loc, const void* w, void* out, msda::FusedArgs fa = msda::FusedArgs{},
+                    int head_major = 0) {
   constexpr int CPL = cpl_of<D, VT>();
   using G = msda::Geom<D * 4 / CPL, THREADS>;
   const int NP = d.L * d.P;
@@ -167,7 +190,7 @@ int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int
   if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
   if (TILED == 3) grid = (unsigned)((int64_t)d.B * d.H * tile2d_bound(d, G::RPC));
   k<<<grid, THREADS, smem, st>>>((const VT*)value, shapes, lsi, (const float*)loc, (const float*)w, (VT*)out, fa,
-                                 d.B, d.S, d.H, d.L, d.Q, d.P, rows);
+                                 d.B, d.S, d.H, d.L, d.Q, d.P, rows, head_major);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
@@ -176,23 +199,28 @@ int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int
 template <int D, typename VT, int PT, int THREADS, int TILED, typename ACC, int PRE = 0>
 int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
                     const int64_t* lsi, const void* loc, const void* w, ACC* gv, void* gl, void* gw,
-                    const msda::DetScale* det, msda::FusedArgs fa = msda::FusedArgs{}) {
+                    const msda::DetScale* det, msda::FusedArgs fa = msda::FusedArgs{}, int coarse_budget = 0,
+                    int head_major = 0) {
   // The backward keeps 4 channels per lane for every type: it is bound by the grad_value reds, and those run
   // fastest as one full 128-byte line per row and instruction (8 channels per lane -> two 64-byte halves per
   // row: 1.75 -> 2.09 ms at cfg2 with bf16 value), so the faster 16-byte gather buys nothing there.
   constexpr int CPL = 4;
   using G = msda::Geom<D * 4 / CPL, THREADS>;
   const int NP = d.L * d.P;
-  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::bwd_row_words(NP, TILED == 1) * 4;
+  static const int exp_pad = exp_env("MSDA_EXP_BWD_SMEM_PAD");
+  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::bwd_row_words(NP, TILED == 1) * 4 + (size_t)exp_pad;
   auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC, PRE, CPL>;
   MSDA_CUDA(ensure_smem(k, smem));
+  static const int exp_carve = exp_env("MSDA_EXP_BWD_CARVEOUT");   // percent of the SM's 228 KB given to shared memory
+  if (exp_carve > 0) MSDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, exp_carve));
   const int64_t rows = d.rows();
   unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
   if (TILED == 1) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
   if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
   if (TILED == 3) grid = (unsigned)((int64_t)d.B * d.H * tile2d_bound(d, G::RPC));
   k<<<grid, THREADS, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
-                                 gv, (float*)gl, (float*)gw, det, fa, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
+                                 gv, (float*)gl, (float*)gw, det, fa, d.B, d.S, d.H, d.L, d.Q, d.P, rows, coarse_budget,
+                                 head_major);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
@@ -226,7 +254,9 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
 
 int fwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* value, const int64_t* shapes,
              const int64_t* lsi, const void* loc, const void* w, void* out) {
-#define CALL_FWD(D_, VT_, PT_, TH_, TL_) launch_fwd_fast<D_, VT_, PT_, TH_, TL_>(st, d, value, shapes, lsi, loc, w, out)
+#define CALL_FWD(D_, VT_, PT_, TH_, TL_)                                                              \
+  launch_fwd_fast<D_, VT_, PT_, TH_, TL_>(st, d, value, shapes, lsi, loc, w, out, msda::FusedArgs{}, \
+                                          (flags & MSDA_FLAG_STRIP_HEAD_MAJOR) ? 1 : 0)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_FWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_FWD);
 #undef CALL_FWD
@@ -234,15 +264,136 @@ int fwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const vo
 
 int bwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* go, const void* value,
              const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl,
-             void* gw) {
+             void* gw, int coarse_budget) {
   // default row order of the backward: STRIP (measured 3 % faster than LINEAR at cfg 2: fewer L1 misses
   // on the crossbar-bound kernel); the forward keeps LINEAR
   if (!(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED | MSDA_FLAG_ORDER_TILE2D))) flags |= MSDA_FLAG_ORDER_STRIP;
 #define CALL_BWD(D_, VT_, PT_, TH_, TL_) \
-  launch_bwd_fast<D_, VT_, PT_, TH_, TL_, float>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw, nullptr)
+  launch_bwd_fast<D_, VT_, PT_, TH_, TL_, float>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw, nullptr, \
+                                                 msda::FusedArgs{}, coarse_budget,                                \
+                                                 (flags & MSDA_FLAG_STRIP_HEAD_MAJOR) ? 1 : 0)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
 #undef CALL_BWD
+}
+
+// ---- shared-memory accumulation of the coarse levels (msda_coarse.cuh) ----
+constexpr int kCoarseBudget = 200 * 1024;   // most shared memory the resident grad_value tile may take
+
+// What the coarse-level accumulation gets for this problem.  budget == 0: not used.  Which levels are resident
+// is decided on the device from the level shapes and the budget; when the caller supplied a HOST copy of the
+// shapes the budget is exactly the resident levels' bytes (so the kernel leaves the rest of the SM's shared
+// memory to the main backward kernel and the two can share every SM), otherwise it is the upper bound and the
+// two kernels run one after the other.
+struct CoarsePlan {
+  int budget = 0;
+  bool exact = false;
+};
+CoarsePlan coarse_plan(const Dims& d, int dtype, unsigned flags, const int64_t* host_shapes) {
+  CoarsePlan p;
+  if (flags & (MSDA_FLAG_COARSE_OFF | MSDA_FLAG_DETERMINISTIC)) return p;
+  if (!fast_ok(d, dtype, flags)) return p;
+  if (!(d.D == 32 || d.D == 64 || d.D == 128)) return p;
+  // Opt-in: measured SLOWER than the all-reds backward at every benchmark shape: a
+  // shared-memory read-modify-write costs the SM's load/store pipe two instructions per 128-byte row where a vector
+  // red costs one, and the resident tile takes the L1 capacity the main kernel's gathers live on.
+  if (!(flags & MSDA_FLAG_COARSE_ON)) return p;
+  const int es = dtype == MSDA_BF16 ? 2 : 4;
+  int cap = 227 * 1024 - 1024 - d.D * 4 - 2 * msda::coarse_stage_bytes(d.D, es, d.L, d.P);
+  if (cap > kCoarseBudget) cap = kCoarseBudget;
+  if (cap < d.D * 4) return p;
+  if (host_shapes) {
+    int Hs[msda::kFastMaxLevels], Ws[msda::kFastMaxLevels];
+    for (int l = 0; l < d.L; ++l) {
+      Hs[l] = (int)host_shapes[2 * l];
+      Ws[l] = (int)host_shapes[2 * l + 1];
+    }
+    const int lc = msda::coarse_first_level(Hs, Ws, d.L, d.D, cap);
+    int64_t bytes = 0;
+    for (int l = lc; l < d.L; ++l) bytes += (int64_t)Hs[l] * Ws[l] * d.D * 4;
+    if (bytes == 0) return p;                       // nothing fits
+    p.budget = (int)bytes;
+    p.exact = true;
+    return p;
+  }
+  const int64_t whole = (int64_t)d.S * d.D * 4;
+  p.budget = (int)(whole < cap ? whole : cap);
+  return p;
+}
+
+int bwd_coarse(cudaStream_t st, const Dims& d, int dtype, const void* go, const int64_t* shapes, const int64_t* lsi,
+               const void* loc, const void* w, float* gv, int budget) {
+  static const int exp_skip = exp_env("MSDA_EXP_SKIP_COARSE_KERNEL");
+  if (exp_skip) return MSDA_OK;
+  MSDA_CUDA(msda::launch_bwd_coarse(st, dtype == MSDA_BF16, go, shapes, lsi, (const float*)loc, (const float*)w, gv, d.B,
+                                    d.S, d.H, d.D, d.L, d.Q, d.P, budget));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MSDA_OK;
+}
+
+// The coarse kernel (1 CTA per SM, most of the SM's shared memory, few warps) and the fast kernel (many small
+// CTAs) use different resources, so they run CONCURRENTLY: the coarse kernel goes first on a library-owned
+// high-priority side stream, the fast kernel fills the rest of every SM from the caller's stream, and the
+// caller's stream then waits for the side stream.  One side stream + event pair per device, created on first
+// use; the fork/join is enqueued under a mutex (cudaStreamWaitEvent binds to the record that precedes it, so
+// re-using the events afterwards is safe).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+constexpr int kMaxDevices = 64;
+SideStream g_side[kMaxDevices];
+std::mutex g_side_mutex;
+
+cudaError_t side_stream(SideStream** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  SideStream& s = g_side[dev];
+  if (!s.stream) {
+    int lo = 0, hi = 0;
+    e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, hi);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  *out = &s;
+  return cudaSuccess;
+}
+
+// fast backward + coarse accumulation, concurrent unless the caller's stream is being captured into a graph
+// (or MSDA_FLAG_COARSE_SERIAL): then both run on the caller's stream, one after the other
+int bwd_fast_with_coarse(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* go, const void* value,
+                         const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl,
+                         void* gw, int budget, bool exact) {
+  bool serial = (flags & MSDA_FLAG_COARSE_SERIAL) != 0 || !exact;
+  if (!serial) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    MSDA_CUDA(cudaStreamIsCapturing(st, &cs));
+    serial = cs != cudaStreamCaptureStatusNone;
+  }
+  if (serial) {
+    if (int s = bwd_fast(st, d, dtype, flags, go, value, shapes, lsi, loc, w, gv, gl, gw, budget)) return s;
+    return bwd_coarse(st, d, dtype, go, shapes, lsi, loc, w, gv, budget);
+  }
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideStream* side = nullptr;
+  MSDA_CUDA(side_stream(&side));
+  MSDA_CUDA(cudaEventRecord(side->fork, st));            // after the caller's zero-fill of grad_value
+  MSDA_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+  int s = bwd_coarse(side->stream, d, dtype, go, shapes, lsi, loc, w, gv, budget);
+  if (s == MSDA_OK) s = bwd_fast(st, d, dtype, flags, go, value, shapes, lsi, loc, w, gv, gl, gw, budget);
+  // join even after a failure so the caller's stream never runs ahead of work already queued on the side stream
+  cudaError_t e = cudaEventRecord(side->join, side->stream);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join, 0);
+  if (s != MSDA_OK) return s;
+  if (e != cudaSuccess) return cuda_fail(e, "joining the coarse-level side stream");
+  return MSDA_OK;
 }
 
 // deterministic accumulate: LINEAR order only
@@ -510,6 +661,16 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
                   int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
                   void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
                   size_t workspace_bytes, int dtype, unsigned flags) {
+  return msda_backward_hs(stream, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                          batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, grad_value,
+                          grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes, dtype, flags, nullptr);
+}
+
+int msda_backward_hs(void* stream, const void* grad_output, const void* value, const int64_t* spatial_shapes,
+                     const int64_t* level_start_index, const void* sampling_loc, const void* attn_weight, int batch,
+                     int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                     void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
+                     size_t workspace_bytes, int dtype, unsigned flags, const int64_t* spatial_shapes_host) {
   g_err[0] = 0;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   if (int s = check_dims(d, dtype)) return s;
@@ -633,8 +794,13 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
 
   int s;
   if (fast_ok(d, dtype, flags)) {
-    s = bwd_fast(st, d, dtype, flags, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                 gv32, grad_sampling_loc, grad_attn_weight);
+    const CoarsePlan plan = coarse_plan(d, dtype, flags, spatial_shapes_host);
+    if (plan.budget > 0)
+      s = bwd_fast_with_coarse(st, d, dtype, flags, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                               attn_weight, gv32, grad_sampling_loc, grad_attn_weight, plan.budget, plan.exact);
+    else
+      s = bwd_fast(st, d, dtype, flags, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                   attn_weight, gv32, grad_sampling_loc, grad_attn_weight, 0);
   } else if (dtype == MSDA_F32) {
     s = bwd_generic<float, float, float>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
                                          attn_weight, gv32, grad_sampling_loc, grad_attn_weight);

@@ -143,11 +143,30 @@ struct LevelTab {
   int tiles_x[kFastMaxLevels];     // TILED only
   int tile_begin[kFastMaxLevels];  // TILED only: first tile index of the level
   int total_tiles;                 // TILED only
-  int pad[3];
+  int first_coarse;                // backward: levels >= this one accumulate grad_value in msda_coarse.cuh, not here
+  int pad[2];
 };
 
+// Backward, shared-memory accumulation of the coarse levels (msda_coarse.cuh): the resident levels are the
+// longest suffix of the pyramid (at most kCoarseMaxLevels) whose pixels x D floats fit in `budget_bytes`.
+// Returns the first resident level, L when nothing fits (or budget == 0: every level goes through reds).
+// Evaluated on the device by both kernels from the same inputs, so they always agree (the host evaluates it too,
+// when it has a copy of the shapes, to size the tile exactly: budget = the resident levels' bytes).
+constexpr int kCoarseMaxLevels = 4;
+__host__ __device__ __forceinline__ int coarse_first_level(const int* Hs, const int* Ws, int L, int D, int budget_bytes) {
+  int lc = L;
+  long long acc = 0;
+  for (int l = L - 1; l >= 0 && L - l <= kCoarseMaxLevels; --l) {
+    acc += (long long)Hs[l] * Ws[l] * D * 4;
+    if (acc > (long long)budget_bytes) break;
+    lc = l;
+  }
+  return lc;
+}
+
 template <int TW, int TH>
-__device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes, const int64_t* lsi, int L) {
+__device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes, const int64_t* lsi, int L, int D = 0,
+                                            int coarse_budget = 0) {
   if (threadIdx.x < L) {
     tab->H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
     tab->W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
@@ -163,6 +182,7 @@ __device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes
       acc += tx * ty;
     }
     tab->total_tiles = acc;
+    tab->first_coarse = coarse_budget > 0 ? coarse_first_level(tab->H, tab->W, L, D, coarse_budget) : L;
   }
   __syncthreads();
 }
@@ -177,6 +197,7 @@ __device__ __forceinline__ void set_single_level(LevelTab* tab, int H, int W) {
     tab->tiles_x[0] = (W + TW - 1) / TW;
     tab->tile_begin[0] = 0;
     tab->total_tiles = tab->tiles_x[0] * ((H + TH - 1) / TH);
+    tab->first_coarse = 1;
   }
   __syncthreads();
 }
@@ -252,6 +273,7 @@ struct RowWalk {
   using G = Geom<D, THREADS>;
   int64_t item, n_items, rows;
   int rin, BH;
+  bool head_major = false;   // STRIP only: items ordered (image, head, strip) instead of (image, strip, head)
   __device__ __forceinline__ RowWalk(const LevelTab* tab, int B, int H, int64_t rows_) : rows(rows_) {
     rin = threadIdx.x / G::LANES;
     item = blockIdx.x;
@@ -267,10 +289,21 @@ struct RowWalk {
     RowRef r;
     if (ORDER == 2) {
       const int chunks = (Q + G::RPC - 1) / G::RPC;
-      const int h = (int)(item % H);
-      const int64_t bc = item / H;
-      const int q = (int)(bc % chunks) * G::RPC + rin;
-      const int b = (int)(bc / chunks);
+      int h, b, q;
+      if (head_major) {
+        // all strips of one (image, head) are adjacent in launch order, so at any moment (nearly) every CTA of
+        // an SM works on the SAME head: that head's coarse levels (35 + 134 KB at DINO-R50 800x1333) then stay
+        // in the SM's L1 and half of the corner gathers stop crossing the crossbar
+        const int64_t bh = item / chunks;
+        q = (int)(item - bh * chunks) * G::RPC + rin;
+        b = (int)(bh / H);
+        h = (int)(bh - (int64_t)b * H);
+      } else {
+        h = (int)(item % H);
+        const int64_t bc = item / H;
+        q = (int)(bc % chunks) * G::RPC + rin;
+        b = (int)(bc / chunks);
+      }
       r.live = q < Q;
       r.b = b;
       r.h = h;
@@ -470,7 +503,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_FWD_MINB : ((
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ w, VT* __restrict__ out, const FusedArgs fused, int B, int S, int H,
-                     int L, int Q, int P, int64_t rows) {
+                     int L, int Q, int P, int64_t rows, int head_major) {
   // FUSED: `loc` holds raw sampling offsets and `w` attention logits (see FusedArgs)
   constexpr int DL = D * 4 / CPL;               // lane geometry: LANES = D / CPL lanes per row
   using G = Geom<DL, THREADS>;
@@ -498,6 +531,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   float* raw_w = my + ((5 * NP + 1) & ~1) + 2 * NP;
 
   RowWalk<DL, THREADS, ORDER> walk(tab, B, H, rows);
+  walk.head_major = head_major != 0;
   if (walk.done()) return;
   RowRef cur = walk.get(tab, L, H, Q);
   if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
@@ -709,7 +743,9 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                      const float* __restrict__ loc, const float* __restrict__ w,
                      ACC* __restrict__ grad_value, float* __restrict__ grad_loc,
                      float* __restrict__ grad_w, const DetScale* __restrict__ det, const FusedArgs fused, int B,
-                     int S, int H, int L, int Q, int P, int64_t rows) {
+                     int S, int H, int L, int Q, int P, int64_t rows, int coarse_budget, int head_major) {
+  // coarse_budget > 0: grad_value of the levels that fit in that many bytes of shared memory is accumulated by
+  // msda_bwd_coarse_kernel (msda_coarse.cuh); this kernel then skips their reds (float accumulation only)
   // FUSED: loc = raw offsets, w = logits in; grad_loc = grad of the offsets, grad_w = grad of the logits out
   constexpr int DL = D * 4 / CPL;
   using G = Geom<DL, THREADS>;
@@ -725,7 +761,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   const int row_words = bwd_row_words(NP, STAGED);
 
   if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
-  else load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
+  else load_levels<G::TW, G::TH>(tab, shapes, lsi, L, D, coarse_budget);
+  const int red_points = tab->first_coarse * P;   // points [0, red_points) scatter with reds here
 
   const int sub = (threadIdx.x & 31) % LANES;
   const int rin = threadIdx.x / LANES;
@@ -741,6 +778,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   // A warp stays converged for the full-mask shuffles below: rows that do not exist (edge tiles,
   // the tail of the last CTA) get all-zero weights, so they scatter nothing and never write.
   RowWalk<DL, THREADS, ORDER> walk(tab, B, H, rows);
+  walk.head_major = head_major != 0;
   if (walk.done()) return;
   RowRef cur = walk.get(tab, L, H, Q);
   if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
@@ -856,7 +894,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             if (cw.y != 0.0f) scatter4_det<LANES>(gimg + o01, cw.y, go_s, gscale);
             if (cw.z != 0.0f) scatter4_det<LANES>(gimg + o10, cw.z, go_s, gscale);
             if (cw.w != 0.0f) scatter4_det<LANES>(gimg + o11, cw.w, go_s, gscale);
-          } else {
+          } else if (pt < red_points) {
             if (cw.x != 0.0f) scatterv<CPL, D / 2>(gsc + o00, cw.x, go_sc);
             if (cw.y != 0.0f) scatterv<CPL, D / 2>(gsc + o01, cw.y, go_sc);
             if (cw.z != 0.0f) scatterv<CPL, D / 2>(gsc + o10, cw.z, go_sc);

@@ -53,6 +53,27 @@ def _flags(backward: bool) -> int:
     return f
 
 
+# Host copies of spatial_shapes, keyed by the device tensor's identity (storage address, version counter, shape).
+# The first backward with a given shapes tensor pays one device->host copy (16 integers); every later call is
+# sync-free.  The copy only sizes launches (msda_backward_hs in include/msda.h), it never enters the arithmetic.
+_host_shapes_cache: dict = {}
+
+
+def _host_shapes(spatial_shapes: torch.Tensor):
+    """ctypes int64 array holding spatial_shapes, or None when it cannot be had without breaking a graph capture."""
+    key = (spatial_shapes.device, spatial_shapes.data_ptr(), spatial_shapes._version, tuple(spatial_shapes.shape))
+    hit = _host_shapes_cache.get(key)
+    if hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        flat = [int(x) for x in spatial_shapes.detach().cpu().reshape(-1).tolist()]
+        hit = (ctypes.c_int64 * len(flat))(*flat)
+        if len(_host_shapes_cache) > 256:
+            _host_shapes_cache.clear()
+        _host_shapes_cache[key] = hit
+    return hit
+
+
 def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr())
 
@@ -120,10 +141,13 @@ def ms_deform_attn_backward(value: torch.Tensor, spatial_shapes: torch.Tensor, l
     ws_bytes = int(handle.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, tag, flags))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
     stream = torch.cuda.current_stream(value.device).cuda_stream
-    status = handle.msda_backward(ctypes.c_void_p(stream), _ptr(grad_output), _ptr(value), _ptr(spatial_shapes),
-                                  _ptr(level_start_index), _ptr(sampling_loc), _ptr(attn_weight), B, S, H, D, L, Q, P,
-                                  _ptr(grad_value), _ptr(grad_loc), _ptr(grad_w),
-                                  _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, tag, flags)
+    host_shapes = _host_shapes(spatial_shapes)
+    status = handle.msda_backward_hs(ctypes.c_void_p(stream), _ptr(grad_output), _ptr(value), _ptr(spatial_shapes),
+                                     _ptr(level_start_index), _ptr(sampling_loc), _ptr(attn_weight), B, S, H, D, L, Q, P,
+                                     _ptr(grad_value), _ptr(grad_loc), _ptr(grad_w),
+                                     _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, tag, flags,
+                                     ctypes.cast(host_shapes, ctypes.c_void_p) if host_shapes is not None
+                                     else ctypes.c_void_p(0))
     _lib.check(status, "ms_deform_attn_backward")
     return [grad_value, grad_loc, grad_w]
 

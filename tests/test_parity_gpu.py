@@ -188,6 +188,98 @@ def test_tile2d_order_on_a_pathological_pyramid():
     assert_close(a[1], b[1], 1e-5, 1e-6, "grad_value")
 
 
+# ------------------------------------------------------------------------------------------------
+# backward: shared-memory accumulation of the coarse levels (csrc/msda_coarse.cuh)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("D,L,P,mode", [(32, 4, 4, "concurrent"), (32, 4, 4, "serial"), (64, 3, 4, "concurrent"),
+                                        (128, 2, 3, "serial"), (32, 5, 8, "concurrent"), (32, 1, 5, "concurrent"),
+                                        (32, 4, 1, "serial"), (64, 4, 6, "concurrent")])
+def test_coarse_level_smem_accumulation(D, L, P, mode, dtype):
+    """grad_value with the coarse levels pre-aggregated in shared memory == the all-reds path == the fp64 oracle;
+    grad_loc / grad_w are untouched by the split (bit-identical)."""
+    _, _lib, _, workloads, msda_c, _ = _mods()
+    levels = [(9, 7), (5, 4), (3, 2), (2, 2), (1, 1)][:L]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 77, 4, D, P, "decoder", "edge", 11, value_dtype=dtype)
+    go = torch.randn(2, 77, 4 * D, generator=torch.Generator().manual_seed(2)).to(dtype)
+    flags = _lib.FLAG_COARSE_ON | (_lib.FLAG_COARSE_SERIAL if mode == "serial" else 0)
+    on = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=flags)
+    off = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_COARSE_OFF)
+    a = [value.float().numpy(), shapes.numpy(), lsi.numpy(), loc.numpy(), w.numpy()]
+    rgv, _, _ = msda_c.backward(go.float().numpy(), *a, np.float64)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert_close(on[1], rgv, tol, 1e-6, "grad_value vs oracle")
+    assert_close(on[1], off[1], tol, 1e-6, "grad_value vs all-reds path")
+    assert np.array_equal(on[2], off[2]) and np.array_equal(on[3], off[3])
+
+
+@pytest.mark.parametrize("dist", ["model", "test", "edge"])
+def test_coarse_levels_partly_resident_many_ctas(dist):
+    """A pyramid whose three coarsest levels (202 240 B at D=32) just fit the 200 KB tile while level 0 does
+    not, enough queries for every CTA to hold a slice, slices that straddle (image, head) boundaries."""
+    _, _lib, _, workloads, msda_c, _ = _mods()
+    levels = [(60, 80), (30, 40), (15, 20), (8, 10)]
+    B, H, D, P, Q = 2, 4, 32, 4, 1531
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, B, Q, H, D, P, "decoder", dist, 5)
+    go = torch.randn(B, Q, H * D, generator=torch.Generator().manual_seed(3))
+    a = [t.numpy() for t in (value, shapes, lsi, loc, w)]
+    rgv, rgl, rgw = msda_c.backward(go.numpy(), *a, np.float64)
+    m = smooth_mask(a[3], a[1], band=1e-4)
+    for flags in (_lib.FLAG_COARSE_ON, _lib.FLAG_COARSE_ON | _lib.FLAG_COARSE_SERIAL,
+                  _lib.FLAG_COARSE_ON | _lib.FLAG_ORDER_LINEAR):
+        _, gv, gl, gw = run_cuda(*a, go, torch.float32, flags=flags)
+        assert_close(gv, rgv, 1e-5, 1e-6, f"grad_value flags={flags}")
+        assert_close(gw, rgw, 1e-5, 1e-6, "grad_w")
+        assert_close(gl * m, rgl * m, 1e-5, 1e-6, "grad_loc")
+
+
+def test_coarse_path_is_opt_in_and_graph_capturable():
+    """Default: one backward kernel.  MSDA_FLAG_COARSE_ON: two (coarse + main), forked onto the library's side
+    stream; under CUDA-graph capture the pair is serialised on the capturing stream and replays give the same
+    gradients."""
+    ir, _lib, functional, workloads, _, _ = _mods()
+    wl = workloads.WORKLOADS["cfg2"]
+    value, shapes, lsi, loc, w = workloads.make_workload_inputs(wl, "model", 2, DEV, batch=1)
+    go = torch.randn(1, wl.queries, wl.num_heads * wl.head_dim, device=DEV)
+    h = _lib.lib()
+    n0 = h.msda_kernel_launch_count()
+    gv0, gl0, gw0 = ir.ms_deform_attn_backward(value, shapes, lsi, loc, w, go, 64)
+    assert h.msda_kernel_launch_count() - n0 == 1
+    with functional.kernel_flags(_lib.FLAG_COARSE_ON):
+        n0 = h.msda_kernel_launch_count()
+        gv, gl, gw = ir.ms_deform_attn_backward(value, shapes, lsi, loc, w, go, 64)
+        assert h.msda_kernel_launch_count() - n0 == 2
+        torch.cuda.synchronize()
+        assert torch.equal(gl, gl0) and torch.equal(gw, gw0)
+        assert_close(gv.double().cpu().numpy(), gv0.double().cpu().numpy(), 1e-5, 1e-6, "grad_value")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ir.ms_deform_attn_backward(value, shapes, lsi, loc, w, go, 64)   # warm-up on the capture stream
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                cgv, cgl, cgw = ir.ms_deform_attn_backward(value, shapes, lsi, loc, w, go, 64)
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(cgl, gl0) and torch.equal(cgw, gw0)
+    assert_close(cgv.double().cpu().numpy(), gv0.double().cpu().numpy(), 1e-5, 1e-6, "grad_value (graph replay)")
+
+
+@pytest.mark.parametrize("order", ["strip", "strip_head_major"])
+def test_strip_head_major_order_agrees(order):
+    _, _lib, _, workloads, msda_c, _ = _mods()
+    levels = [(9, 7), (5, 4), (3, 2)]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 77, 4, 32, 4, "decoder", "edge", 13)
+    go = torch.randn(2, 77, 4 * 32, generator=torch.Generator().manual_seed(4))
+    flags = _lib.FLAG_ORDER_STRIP | (_lib.FLAG_STRIP_HEAD_MAJOR if order == "strip_head_major" else 0)
+    got = run_cuda(value, shapes, lsi, loc, w, go, flags=flags)
+    ref = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_ORDER_LINEAR)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3])
+    assert_close(got[1], ref[1], 1e-5, 1e-6, "grad_value")
+
+
 @pytest.mark.parametrize("dtype,D", [(torch.float32, 32), (torch.bfloat16, 32), (torch.float32, 30), (torch.float64, 32),
                                      (torch.float32, 64)])
 def test_deterministic_backward_is_bit_reproducible(dtype, D):
