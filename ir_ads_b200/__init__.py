@@ -10,6 +10,7 @@ from .functional import (  # noqa: F401
     kernel_flags,
     ms_deform_attn_backward,
     ms_deform_attn_forward,
+    multi_scale_deformable_attn_pytorch,
     set_deterministic,
 )
 from .dcnv3 import DCNv3Function, dcnv3_backward, dcnv3_forward  # noqa: F401
@@ -20,6 +21,7 @@ __all__ = [
     "MultiScaleDeformableAttnFunction",
     "ms_deform_attn_forward",
     "ms_deform_attn_backward",
+    "multi_scale_deformable_attn_pytorch",
     "set_deterministic",
     "kernel_flags",
     "DCNv3Function",

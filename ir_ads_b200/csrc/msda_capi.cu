@@ -684,7 +684,10 @@ int msda_backward_hs(void* stream, const void* grad_output, const void* value, c
   MSDA_CUDA(guard.enter(anchor));
   const bool det = (flags & MSDA_FLAG_DETERMINISTIC) != 0;
   const bool have_samples = d.n_points() != 0 && d.n_value() != 0;
-  if (d.n_value() && !(det && have_samples)) {   // the deterministic path writes grad_value in its finalize pass
+  // zero-fill grad_value -- unless a later pass writes every element anyway: the deterministic finalize / gather,
+  // or the float -> bf16 conversion of the workspace accumulators
+  const bool overwritten = have_samples && d.D != 0 && (det || dtype == MSDA_BF16);
+  if (d.n_value() && !overwritten) {
     if (!grad_value) return fail(MSDA_ERR_INVALID_ARGUMENT, "grad_value is null");
     MSDA_CUDA(cudaMemsetAsync(grad_value, 0, (size_t)d.n_value() * es, st));
   }

@@ -175,6 +175,20 @@ class MultiScaleDeformableAttnFunction(Function):
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
 
 
+def multi_scale_deformable_attn_pytorch(value: torch.Tensor, value_spatial_shapes: torch.Tensor,
+                                        sampling_locations: torch.Tensor, attention_weights: torch.Tensor) -> torch.Tensor:
+    """Same name, arguments and result as the reference's grid_sample formulation
+    (/root/reference/detrex/layers/multi_scale_deform_attn.py:96-136), computed by the CUDA kernels: callers that
+    import this function (the reference's tests do, tests/test_ms_deform_attn.py:20) keep working, differentiably.
+    There is still no CPU path: CPU tensors raise.  ``level_start_index`` is derived on the device (no sync)."""
+    _require(value.is_cuda, "Not implemented on the CPU")
+    shapes = value_spatial_shapes.to(device=value.device, dtype=torch.int64).contiguous()
+    sizes = shapes[:, 0] * shapes[:, 1]
+    level_start_index = torch.cat((sizes.new_zeros((1,)), sizes.cumsum(0)[:-1]))
+    return MultiScaleDeformableAttnFunction.apply(value.contiguous(), shapes, level_start_index,
+                                                  sampling_locations.contiguous(), attention_weights.contiguous(), 64)
+
+
 # ------------------------------------------------------------------------------------------------
 # fused module path (SURVEY.md section 8f-1): softmax + sampling-location arithmetic inside the kernels
 # ------------------------------------------------------------------------------------------------

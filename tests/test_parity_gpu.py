@@ -454,6 +454,23 @@ def test_full_size_properties(cfg):
         assert_close(got, ref, rt, 1e-6, f"{cfg} rows b={b}")
 
 
+def test_pytorch_named_entry_point(golden):
+    """multi_scale_deformable_attn_pytorch(value, shapes, loc, w) -- the reference's other public function
+    (multi_scale_deform_attn.py:96-136) -- runs on the kernels and matches the reference-made vectors."""
+    ir, *_ = _mods()
+    c = golden("ref_test")
+    v = torch.as_tensor(c["value"]).to(DEV, torch.float64).requires_grad_(True)
+    out = ir.multi_scale_deformable_attn_pytorch(v, torch.as_tensor(c["shapes"]).to(DEV),
+                                                 torch.as_tensor(c["loc"]).to(DEV, torch.float64),
+                                                 torch.as_tensor(c["w"]).to(DEV, torch.float64))
+    out.backward(torch.as_tensor(c["grad_out"]).to(DEV, torch.float64))
+    assert np.allclose(out.detach().cpu().numpy(), c["f64/out"], rtol=1e-5, atol=1e-8)
+    assert nerr(v.grad.cpu().numpy(), c["f64/grad_value"]) < 1e-12
+    with pytest.raises(RuntimeError, match="CPU"):
+        ir.multi_scale_deformable_attn_pytorch(torch.as_tensor(c["value"]), torch.as_tensor(c["shapes"]),
+                                               torch.as_tensor(c["loc"]), torch.as_tensor(c["w"]))
+
+
 # ------------------------------------------------------------------------------------------------
 # edge behaviour (SURVEY appendix B)
 # ------------------------------------------------------------------------------------------------
