@@ -80,14 +80,19 @@ struct DeviceGuard {
   }
 };
 
-// Experiment knobs (tools/ only; results with MSDA_EXP_SKIP_COARSE_KERNEL are WRONG on purpose):
+// Experiment knobs, compiled in only with -DMSDA_EXPERIMENTS (tools/ablate.sh builds such variants into
+// build/variants/, never the product library; results with MSDA_EXP_SKIP_COARSE_KERNEL are WRONG on purpose):
 //   MSDA_EXP_BWD_SMEM_PAD=<bytes>   extra dynamic shared memory per CTA of the main backward kernel (occupancy study)
 //   MSDA_EXP_BWD_CARVEOUT=<percent> preferred shared-memory carveout of the main backward kernel (L1 size study)
 //   MSDA_EXP_SKIP_COARSE_KERNEL=1   plan the coarse-level split but do not launch the coarse kernel (times the rest)
+#ifdef MSDA_EXPERIMENTS
 int exp_env(const char* name) {
   const char* v = std::getenv(name);
   return v ? std::atoi(v) : 0;
 }
+#else
+constexpr int exp_env(const char*) { return 0; }
+#endif
 
 struct Dims {
   int B, S, H, D, L, Q, P;

@@ -9,6 +9,7 @@ tail -15 "$out/pytest_coarse.log"
 timeout 600 python tools/sweep.py --workloads cfg2 --dists model,test --flags 0,128,512 --iters 10 > "$out/sweep_coarse_cfg2.jsonl" 2>&1
 cat "$out/sweep_coarse_cfg2.jsonl"
 echo "--- main kernel alone (coarse kernel skipped), 4 / 3 / 2 CTAs per SM"
+export MSDA_B200_LIB=build/variants/lib_knobs.so   # tools/ablate.sh builds it
 for pad in 0 43000 63000; do
   MSDA_EXP_SKIP_COARSE_KERNEL=1 MSDA_EXP_BWD_SMEM_PAD=$pad timeout 300 python tools/sweep.py --workloads cfg2 --flags 512 --iters 10 2>&1 | tail -1
 done
