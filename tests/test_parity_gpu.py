@@ -454,6 +454,47 @@ def test_full_size_properties(cfg):
         assert_close(got, ref, rt, 1e-6, f"{cfg} rows b={b}")
 
 
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_random_problem_shapes_against_oracle(seed):
+    """Seeded fuzz over (levels, B, Q, H, D, P, dtype, distribution, flags): forward and all three gradients against the
+    fp64 C oracle, through whichever kernels the shape dispatches to (fast, generic, every row order, coarse split)."""
+    _, _lib, _, workloads, msda_c, _ = _mods()
+    rng = np.random.default_rng(1000 + seed)
+    L = int(rng.integers(1, 6))
+    levels, h, w = [], int(rng.integers(3, 40)), int(rng.integers(3, 40))
+    for _ in range(L):
+        levels.append((h, w))
+        h, w = max(1, (h + 1) // 2), max(1, (w + 1) // 2)
+    B, H = int(rng.integers(1, 4)), int(rng.choice([1, 2, 4, 8]))
+    D = int(rng.choice([16, 32, 64, 128, 8, 24, 40]))
+    P = int(rng.integers(1, 9))
+    encoder = bool(rng.integers(0, 2))
+    Q = 0 if encoder else int(rng.integers(1, 200))
+    dist = str(rng.choice(["model", "test", "edge"]))
+    dtype = torch.bfloat16 if (rng.integers(0, 4) == 0) else torch.float32
+    flag_choices = [0, _lib.FLAG_ORDER_LINEAR, _lib.FLAG_ORDER_STRIP, _lib.FLAG_ORDER_STRIP | _lib.FLAG_STRIP_HEAD_MAJOR,
+                    _lib.FLAG_COARSE_ON, _lib.FLAG_COARSE_ON | _lib.FLAG_COARSE_SERIAL, _lib.FLAG_FORCE_GENERIC]
+    if encoder:
+        flag_choices += [_lib.FLAG_ORDER_TILED, _lib.FLAG_ORDER_TILE2D]
+    flags = int(rng.choice(flag_choices))
+    value, shapes, lsi, loc, wgt = workloads.make_inputs(levels, B, Q, H, D, P, "encoder" if encoder else "decoder", dist,
+                                                         seed, value_dtype=dtype)
+    Qn = loc.shape[1]
+    go = torch.randn(B, Qn, H * D, generator=torch.Generator().manual_seed(seed)).to(dtype)
+    a = [value.float().numpy(), shapes.numpy(), lsi.numpy(), loc.numpy(), wgt.numpy()]
+    ref_out = msda_c.forward(*a, np.float64)
+    rgv, rgl, rgw = msda_c.backward(go.float().numpy(), *a, np.float64)
+    m = smooth_mask(a[3], a[1], band=1e-4)
+    out, gv, gl, gw = run_cuda(value, shapes, lsi, loc, wgt, go, dtype, flags=flags)
+    what = f"levels={levels} B={B} Q={Qn} H={H} D={D} P={P} {dist} {dtype} flags={flags}"
+    vt = 1e-5 if dtype == torch.float32 else 1e-2
+    at = 1e-5 if dtype == torch.float32 else 1e-4
+    assert_close(out, ref_out, vt, 1e-6, "out " + what)
+    assert_close(gv, rgv, vt, 1e-6, "grad_value " + what)
+    assert_close(gw, rgw, at, 1e-6, "grad_w " + what)
+    assert_close(gl * m, rgl * m, at, 1e-6, "grad_loc " + what)
+
+
 def test_pytorch_named_entry_point(golden):
     """multi_scale_deformable_attn_pytorch(value, shapes, loc, w) -- the reference's other public function
     (multi_scale_deform_attn.py:96-136) -- runs on the kernels and matches the reference-made vectors."""

@@ -1,9 +1,10 @@
 #!/usr/bin/env bash
-# experiment: persistent TILED order with 256-thread CTAs (6 per SM) vs the 1024-thread one vs LINEAR
+# ncu --set full of the opt-in coarse-level pair (serial mode: flags 256|512 = 768): the coarse kernel and the main
+# backward kernel with the coarse reds skipped
 set -u
 out=gpurun_out
 mkdir -p "$out"
-S="timeout 300 python tools/sweep.py --iters 10"
-$S --workloads cfg2 --flags 0,8 2>&1 | tail -2
-MSDA_EXP_TILED_256=1 $S --workloads cfg2,cfg5 --flags 8 2>&1 | tail -2
-timeout 900 python -m pytest tests -m gpu -x -q -k "pytorch_named or bf16 or tiled" 2>&1 | tail -3
+P="python tools/sweep.py --workloads cfg2 --flags 768 --iters 2"
+$P > "$out/prof_coarse_plain.log" 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:msda_bwd -s 6 -c 2 -f -o "$out/prof_coarse_pair" $P > "$out/ncu_coarse_pair.log" 2>&1
+tail -3 "$out/ncu_coarse_pair.log"
