@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 1
+#define MSDA_ABI_VERSION 2
 
 /* dtype tags */
 #define MSDA_F32 0  /* value/out/grads float,  loc/w float  */
@@ -146,6 +146,13 @@ int msda_backward_hs(void* stream, const void* grad_output, const void* value,
  *   attn_logits       [B, Q, H, L*P]     float  raw output of its attention_weights Linear (pre-softmax)
  *   reference_points  [B, Q, L, ref_dim] float  ref_dim 2: loc = ref + off / (W_l, H_l)   (py:320-324)
  *                                               ref_dim 4: loc = ref_xy + off / P * ref_wh * 0.5 (py:326-332)
+ *   value_padding_mask [B, S] uint8, or NULL    the module's key_padding_mask (non-zero = padded pixel): its
+ *                                               value.masked_fill(key_padding_mask[..., None], 0) (py:291-292)
+ *                                               is folded into the kernels -- a masked pixel's value row reads
+ *                                               as zeros in the output and in every gradient, and its
+ *                                               grad_value is 0 -- so `value` is passed UNMASKED and the
+ *                                               masked copy (one read + one write of value per layer, and the
+ *                                               same again in backward) never exists
  * Backward returns grad_value plus the gradients w.r.t. the two RAW tensors (what the Linear layers'
  * backward consumes); it uses the same workspace rule as msda_backward.  Only the fast kernels have
  * a fused form: otherwise MSDA_ERR_UNSUPPORTED is returned (query with msda_fused_supported) and the
@@ -155,16 +162,18 @@ int msda_fused_supported(int channels, int num_levels, int num_point, int spatia
                          int dtype, unsigned flags);
 int msda_fused_forward(void* stream, const void* value, const int64_t* spatial_shapes,
                        const int64_t* level_start_index, const float* sampling_offsets,
-                       const float* attn_logits, const float* reference_points, int ref_dim, int batch,
-                       int spatial_size, int num_heads, int channels, int num_levels, int num_query,
-                       int num_point, void* output, int dtype, unsigned flags);
+                       const float* attn_logits, const float* reference_points, int ref_dim,
+                       const uint8_t* value_padding_mask, int batch, int spatial_size, int num_heads,
+                       int channels, int num_levels, int num_query, int num_point, void* output, int dtype,
+                       unsigned flags);
 int msda_fused_backward(void* stream, const void* grad_output, const void* value,
                         const int64_t* spatial_shapes, const int64_t* level_start_index,
                         const float* sampling_offsets, const float* attn_logits,
-                        const float* reference_points, int ref_dim, int batch, int spatial_size,
-                        int num_heads, int channels, int num_levels, int num_query, int num_point,
-                        void* grad_value, float* grad_offsets, float* grad_logits, void* workspace,
-                        size_t workspace_bytes, int dtype, unsigned flags);
+                        const float* reference_points, int ref_dim, const uint8_t* value_padding_mask,
+                        int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                        int num_query, int num_point, void* grad_value, float* grad_offsets,
+                        float* grad_logits, void* workspace, size_t workspace_bytes, int dtype,
+                        unsigned flags);
 
 /*
  * DCNv3 core op: the other native op of detrex._C, same gather/scatter core.

@@ -29,7 +29,7 @@ FLAG_COARSE_OFF = 1 << 7
 FLAG_COARSE_ON = 1 << 8
 FLAG_COARSE_SERIAL = 1 << 9
 FLAG_STRIP_HEAD_MAJOR = 1 << 10
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lock = threading.Lock()
 _lib = None
@@ -66,10 +66,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_fused_supported.restype = i
     lib.msda_fused_supported.argtypes = [i, i, i, i, i, i, u]
     lib.msda_fused_forward.restype = i
-    lib.msda_fused_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp, i, u]
+    lib.msda_fused_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, vp, i, i, i, i, i, i, i, vp, i, u]
     lib.msda_fused_backward.restype = i
-    lib.msda_fused_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, sz,
-                                        i, u]
+    lib.msda_fused_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, vp, i, i, i, i, i, i, i, vp, vp, vp, vp,
+                                        sz, i, u]
     lib.msda_debug_bookkeeping.restype = i
     lib.msda_debug_bookkeeping.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]
     lib.msda_status_string.restype = ctypes.c_char_p

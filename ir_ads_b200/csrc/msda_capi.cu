@@ -839,9 +839,9 @@ int msda_fused_supported(int channels, int num_levels, int num_point, int spatia
 
 int msda_fused_forward(void* stream, const void* value, const int64_t* spatial_shapes,
                        const int64_t* level_start_index, const float* sampling_offsets, const float* attn_logits,
-                       const float* reference_points, int ref_dim, int batch, int spatial_size, int num_heads,
-                       int channels, int num_levels, int num_query, int num_point, void* output, int dtype,
-                       unsigned flags) {
+                       const float* reference_points, int ref_dim, const uint8_t* value_padding_mask, int batch,
+                       int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                       void* output, int dtype, unsigned flags) {
   g_err[0] = 0;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   if (int s = check_dims(d, dtype)) return s;
@@ -858,16 +858,17 @@ int msda_fused_forward(void* stream, const void* value, const int64_t* spatial_s
   fa.ref = reference_points;
   fa.ref_dim = ref_dim;
   fa.inv_P = 1.0f / (float)num_point;
+  fa.value_mask = value_padding_mask;
   return fwd_fused(static_cast<cudaStream_t>(stream), d, dtype, value, spatial_shapes, level_start_index,
                    sampling_offsets, attn_logits, output, fa);
 }
 
 int msda_fused_backward(void* stream, const void* grad_output, const void* value, const int64_t* spatial_shapes,
                         const int64_t* level_start_index, const float* sampling_offsets, const float* attn_logits,
-                        const float* reference_points, int ref_dim, int batch, int spatial_size, int num_heads,
-                        int channels, int num_levels, int num_query, int num_point, void* grad_value,
-                        float* grad_offsets, float* grad_logits, void* workspace, size_t workspace_bytes, int dtype,
-                        unsigned flags) {
+                        const float* reference_points, int ref_dim, const uint8_t* value_padding_mask, int batch,
+                        int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
+                        void* grad_value, float* grad_offsets, float* grad_logits, void* workspace,
+                        size_t workspace_bytes, int dtype, unsigned flags) {
   g_err[0] = 0;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   if (int s = check_dims(d, dtype)) return s;
@@ -892,6 +893,7 @@ int msda_fused_backward(void* stream, const void* grad_output, const void* value
   fa.ref = reference_points;
   fa.ref_dim = ref_dim;
   fa.inv_P = 1.0f / (float)num_point;
+  fa.value_mask = value_padding_mask;
   if (int s = bwd_fused(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_offsets,
                         attn_logits, gv32, grad_offsets, grad_logits, fa))
     return s;

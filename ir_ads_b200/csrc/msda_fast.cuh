@@ -365,6 +365,7 @@ struct RowWalk {
 struct PointRec {
   float4 cw;   // corner weights (v1..v4 of cuh:56-80) x attention weight, 0 where padded
   int oc;
+  int pix;       // pixel index (inside the image) of the clamped low corner: oc == ((pix*H + h)*D) | flags
   float lw, lh;  // fractional parts; lw < 0 marks a gated-out point
 };
 
@@ -408,7 +409,8 @@ __device__ __forceinline__ PointRec record_from_cell(const Cell<float> c, float 
   const int xc = gated ? 0 : max(c.x0, 0), yc = gated ? 0 : max(c.y0, 0);
   int flags = 0;
   if (!gated) flags = (int)(x0v && x1v) | ((int)(y0v && y1v) << 1) | ((int)x0v << 2) | ((int)y0v << 3);
-  r.oc = (((start + yc * Wl + xc) * H + h) * D) | flags;
+  r.pix = start + yc * Wl + xc;
+  r.oc = ((r.pix * H + h) * D) | flags;
   r.lw = gated ? -1.0f : c.lw;
   r.lh = c.lh;
   return r;
@@ -423,6 +425,10 @@ __device__ __forceinline__ PointRec record_from_cell(const Cell<float> c, float 
 // bit-identical to the unfused module's.
 struct FusedArgs {
   const float* ref;   // reference_points [B, Q, L, ref_dim]
+  // key_padding_mask [B, S] (one byte per pixel, non-zero = padded), or null: the module's
+  // value.masked_fill(key_padding_mask[..., None], 0) (multi_scale_deform_attn.py:291-292) folded into the
+  // kernels -- a masked pixel's row reads as zeros, see apply_value_mask
+  const unsigned char* value_mask;
   int ref_dim;        // 2: loc = ref + off / (W_l, H_l);  4: loc = ref_xy + off / P * ref_wh * 0.5
   float inv_P;        // 1 / P
   // PRE == 2 (DCNv3): the same gather/scatter core driven by a convolution-style
@@ -449,6 +455,28 @@ __device__ __forceinline__ float2 fused_location(const float2 off, const float* 
     loc.y = __fadd_rn(__ldg(r + 1), __fmul_rn(__fmul_rn(__fmul_rn(off.y, inv_P), __ldg(r + 3)), 0.5f));
   }
   return loc;
+}
+
+// Padding mask folded into the records.  A masked pixel's value row counts as zeros, so its corner weight becomes
+// zero: the forward then adds nothing for it and the backward scatters nothing into it (grad_value of a masked
+// pixel stays 0, which is masked_fill's own backward).  Backward's finalize step must also treat that corner's
+// VALUE as 0 in grad_sampling_loc / grad_attn_weight, whereas a corner whose weight merely happens to be 0
+// (lw == 0, say) still enters the location gradient.  The two are told apart by the zero's sign: masked corners
+// carry -0.0f, every other zero weight is canonicalised to +0.0f (x + 0.0f maps -0 to +0 and nothing else).
+// The row is still loaded, so a non-finite value under the mask would propagate (the reference's masked_fill
+// discards it); values there come out of value_proj and are finite.
+__device__ __forceinline__ void apply_value_mask(PointRec& r, const unsigned char* mask_img, int Wl) {
+  const int dx = r.oc & 1, dy = (r.oc & 2) ? Wl : 0;
+  const bool m00 = __ldg(mask_img + r.pix) != 0, m01 = __ldg(mask_img + r.pix + dx) != 0;
+  const bool m10 = __ldg(mask_img + r.pix + dy) != 0, m11 = __ldg(mask_img + r.pix + dy + dx) != 0;
+  r.cw.x = m00 ? -0.0f : __fadd_rn(r.cw.x, 0.0f);
+  r.cw.y = m01 ? -0.0f : __fadd_rn(r.cw.y, 0.0f);
+  r.cw.z = m10 ? -0.0f : __fadd_rn(r.cw.z, 0.0f);
+  r.cw.w = m11 ? -0.0f : __fadd_rn(r.cw.w, 0.0f);
+}
+__device__ __forceinline__ unsigned masked_corners(const float4 cw) {
+  return (unsigned)(__float_as_uint(cw.x) == 0x80000000u) | ((unsigned)(__float_as_uint(cw.y) == 0x80000000u) << 1) |
+         ((unsigned)(__float_as_uint(cw.z) == 0x80000000u) << 2) | ((unsigned)(__float_as_uint(cw.w) == 0x80000000u) << 3);
 }
 
 // DCNv3 sampling position of kernel point `pt` (= i*kernel_h + j, i over kernel_w) for output pixel q,
@@ -570,6 +598,9 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
             r = record_from_cell(locate_pixel(px.x, px.y, tab->H[0], tab->W[0]), aw, tab->H[0], tab->W[0], 0, H, cur.h, D);
           } else {
             r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+          }
+          if constexpr (FUSED) {
+            if (fused.value_mask) apply_value_mask(r, fused.value_mask + (int64_t)cur.b * S, tab->W[l]);
           }
           s_cw[pt] = r.cw;
           s_oc[pt] = r.oc;
@@ -822,6 +853,9 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           } else {
             r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
           }
+          if constexpr (FUSED) {
+            if (fused.value_mask) apply_value_mask(r, fused.value_mask + (int64_t)cur.b * S, tab->W[l]);
+          }
           cw = r.cw;
           fin = make_int4(r.oc, __float_as_int(r.lw), __float_as_int(r.lh), __float_as_int(aw));
         }
@@ -914,9 +948,13 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         if (lw >= 0.0f) {
           const bool x0v = (r.x & 4) != 0, y0v = (r.x & 8) != 0;
           const bool x1v = (r.x & 1) != 0 || !x0v, y1v = (r.x & 2) != 0 || !y0v;
-          // d[k] = <grad_out, v_k>; padded corners contribute 0 (cuh:119-158)
-          const float d0 = (x0v && y0v) ? d[0] : 0.0f, d1 = (x1v && y0v) ? d[1] : 0.0f;
-          const float d2 = (x0v && y1v) ? d[2] : 0.0f, d3 = (x1v && y1v) ? d[3] : 0.0f;
+          unsigned msk = 0;   // FUSED with a padding mask: corners whose value row reads as zeros
+          if constexpr (FUSED) {
+            if (fused.value_mask) msk = masked_corners(s_cw[mine]);
+          }
+          // d[k] = <grad_out, v_k>; padded (and masked) corners contribute 0 (cuh:119-158)
+          const float d0 = (x0v && y0v && !(msk & 1u)) ? d[0] : 0.0f, d1 = (x1v && y0v && !(msk & 2u)) ? d[1] : 0.0f;
+          const float d2 = (x0v && y1v && !(msk & 4u)) ? d[2] : 0.0f, d3 = (x1v && y1v && !(msk & 8u)) ? d[3] : 0.0f;
           const float hh = 1.0f - lh, hw = 1.0f - lw;
           const int l = level_of<PT>(mine, P);
           g_aw = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;

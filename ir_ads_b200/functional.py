@@ -202,15 +202,23 @@ def fused_supported(value: torch.Tensor, num_levels: int, num_points: int) -> bo
                                                 _flags(True)))
 
 
+def _mask_ptr(mask) -> ctypes.c_void_p:
+    return _ptr(mask) if mask is not None else ctypes.c_void_p(0)
+
+
 class MSDeformAttnFusedFunction(Function):
-    """``apply(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points)``
-    -> ``[B, Q, H*D]``.  ``sampling_offsets [B,Q,H,L,P,2]`` and ``attn_logits [B,Q,H,L*P]`` are the raw
-    outputs of the module's two Linear layers (float32); ``reference_points [B,Q,L,2|4]`` float32.
-    Equivalent to softmax + location affine (multi_scale_deform_attn.py:300-332) followed by
-    MultiScaleDeformableAttnFunction, without materialising locations / weights or their gradients."""
+    """``apply(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+    key_padding_mask=None)`` -> ``[B, Q, H*D]``.  ``sampling_offsets [B,Q,H,L,P,2]`` and ``attn_logits
+    [B,Q,H,L*P]`` are the raw outputs of the module's two Linear layers (float32); ``reference_points
+    [B,Q,L,2|4]`` float32.  Equivalent to softmax + location affine (multi_scale_deform_attn.py:300-332)
+    followed by MultiScaleDeformableAttnFunction, without materialising locations / weights or their
+    gradients.  With ``key_padding_mask [B,S]`` (bool or uint8, True = padded) it is additionally equivalent
+    to ``value.masked_fill(key_padding_mask[..., None, None], 0)`` in front of that (py:291-292): ``value`` is
+    passed unmasked, masked pixels read as zeros inside the kernels and receive a zero ``grad_value``."""
 
     @staticmethod
-    def forward(ctx, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points):
+    def forward(ctx, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                key_padding_mask=None):
         B, S, H, D = value.shape
         _, Q, _, L, P, _ = sampling_offsets.shape
         for name, t in (("value", value), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
@@ -224,14 +232,22 @@ class MSDeformAttnFusedFunction(Function):
         ref_dim = reference_points.shape[-1]
         _require(tuple(reference_points.shape) == (B, Q, L, ref_dim) and ref_dim in (2, 4),
                  "reference_points must be [B, Q, L, 2 or 4]")
+        mask = None
+        if key_padding_mask is not None:
+            _require(key_padding_mask.dtype in (torch.bool, torch.uint8), "key_padding_mask must be bool or uint8")
+            _require(tuple(key_padding_mask.shape) == (B, S), "key_padding_mask must be [B, S]")
+            _require(key_padding_mask.is_cuda and key_padding_mask.device == value.device,
+                     f"key_padding_mask must be a CUDA tensor on {value.device}")
+            mask = key_padding_mask.contiguous()   # one byte per pixel either way; non-zero = padded
         out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
         stream = torch.cuda.current_stream(value.device).cuda_stream
         status = _lib.lib().msda_fused_forward(
             ctypes.c_void_p(stream), _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_offsets),
-            _ptr(attn_logits), _ptr(reference_points), ref_dim, B, S, H, D, L, Q, P, _ptr(out),
+            _ptr(attn_logits), _ptr(reference_points), ref_dim, _mask_ptr(mask), B, S, H, D, L, Q, P, _ptr(out),
             _DTYPE_TAG[value.dtype], _flags(False))
         _lib.check(status, "msda_fused_forward")
         ctx.save_for_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points)
+        ctx.value_mask = mask
         return out
 
     @staticmethod
@@ -253,9 +269,9 @@ class MSDeformAttnFusedFunction(Function):
         stream = torch.cuda.current_stream(value.device).cuda_stream
         status = handle.msda_fused_backward(
             ctypes.c_void_p(stream), _ptr(grad_output), _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
-            _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points), ref_dim, B, S, H, D, L, Q, P,
-            _ptr(grad_value), _ptr(grad_off), _ptr(grad_logits), _ptr(ws) if ws is not None else ctypes.c_void_p(0),
-            ws_bytes, tag, flags)
+            _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points), ref_dim, _mask_ptr(ctx.value_mask),
+            B, S, H, D, L, Q, P, _ptr(grad_value), _ptr(grad_off), _ptr(grad_logits),
+            _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, tag, flags)
         _lib.check(status, "msda_fused_backward")
         grad_ref = None
         if ctx.needs_input_grad[5]:
@@ -270,7 +286,7 @@ class MSDeformAttnFusedFunction(Function):
                 g_xy = g_loc.sum(dim=(2, 4))
                 g_wh = (g_loc * sampling_offsets * (0.5 / P)).sum(dim=(2, 4))
                 grad_ref = torch.cat([g_xy, g_wh], -1)
-        return grad_value, None, None, grad_off, grad_logits, grad_ref
+        return grad_value, None, None, grad_off, grad_logits, grad_ref, None
 
 
 def debug_bookkeeping(sampling_loc: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,

@@ -117,9 +117,6 @@ class MultiScaleDeformableAttention(nn.Module):
         H, L, P = self.num_heads, self.num_levels, self.num_points
 
         value = self.value_proj(value)
-        if key_padding_mask is not None:
-            value = value.masked_fill(key_padding_mask[..., None], float(0))
-        value = value.view(bs, num_value, H, -1)
         if not value.is_cuda:
             raise RuntimeError("MultiScaleDeformableAttention: Not implemented on the CPU "
                                "(the B200 build has no PyTorch fallback)")
@@ -130,12 +127,18 @@ class MultiScaleDeformableAttention(nn.Module):
         logits = self.attention_weights(query).view(bs, num_query, H, L * P)
 
         io_dtype = value.dtype
+        value = value.view(bs, num_value, H, -1)
         if io_dtype == torch.float16:
             value = value.float()
-        if self.fuse_pre_ops and fused_supported(value, L, P):
+        fused = self.fuse_pre_ops and fused_supported(value, L, P)
+        if key_padding_mask is not None and not fused:
+            value = value.masked_fill(key_padding_mask[..., None, None], float(0))
+        if fused:
+            # the padding mask goes into the kernels (masked pixels read as zeros, zero grad_value): the masked
+            # copy of value (py:291-292) and its backward never exist
             output = MSDeformAttnFusedFunction.apply(
                 value.contiguous(), spatial_shapes, level_start_index, offsets.float().contiguous(),
-                logits.float().contiguous(), reference_points.float().contiguous())
+                logits.float().contiguous(), reference_points.float().contiguous(), key_padding_mask)
             if output.dtype != io_dtype:
                 output = output.to(io_dtype)
             output = self.output_proj(output)

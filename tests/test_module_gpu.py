@@ -171,6 +171,56 @@ def test_fused_function_matches_composition(ref_dim, D, L, P, dtype):
     close(leaves_a[3].grad, leaves_b[3].grad, "grad_reference_points", 1e-4 if dtype == torch.float32 else tol)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ref_dim,D,L,P", [(2, 32, 4, 4), (4, 32, 4, 4), (2, 64, 3, 8), (4, 16, 2, 3)])
+def test_fused_function_folds_the_padding_mask(ref_dim, D, L, P, dtype):
+    """key_padding_mask inside the kernels == value.masked_fill(mask, 0) in front of the op (py:291-292):
+    same output, same gradients for offsets / logits / reference points, zero grad_value under the mask."""
+    from ir_ads_b200.functional import MSDeformAttnFusedFunction
+    from ir_ads_b200.workloads import level_tensors
+
+    torch.manual_seed(11)
+    levels = [(11, 17), (6, 9), (3, 5), (2, 3)][:L]
+    shapes, lsi = level_tensors(levels, DEV)
+    S = sum(h * w for h, w in levels)
+    B, Q, H = 3, 47, 4
+    value = torch.randn(B, S, H, D, device=DEV).to(dtype)
+    offsets = torch.randn(B, Q, H, L, P, 2, device=DEV) * 3.0
+    logits = torch.randn(B, Q, H, L * P, device=DEV) * 2.0
+    ref = torch.rand(B, Q, L, ref_dim, device=DEV) * 1.2 - 0.1
+    if ref_dim == 4:
+        ref[..., 2:] = ref[..., 2:].abs() * 0.4 + 0.05
+    go = torch.randn(B, Q, H * D, device=DEV).to(dtype)
+    # image 0: batch-padding pattern (right and bottom margins of every level); image 1: random 30 %; image 2: none
+    mask = torch.zeros(B, S, dtype=torch.bool, device=DEV)
+    start = 0
+    for h, w in levels:
+        m = torch.zeros(h, w, dtype=torch.bool, device=DEV)
+        m[:, (2 * w) // 3:] = True
+        m[(3 * h) // 4:, :] = True
+        mask[0, start:start + h * w] = m.reshape(-1)
+        start += h * w
+    mask[1] = torch.rand(S, device=DEV) < 0.3
+
+    leaves_a = [t.clone().requires_grad_(True) for t in (value, offsets, logits, ref)]
+    out_a = MSDeformAttnFusedFunction.apply(leaves_a[0], shapes, lsi, leaves_a[1], leaves_a[2], leaves_a[3], mask)
+    out_a.backward(go)
+    leaves_b = [t.clone().requires_grad_(True) for t in (value, offsets, logits, ref)]
+    out_b = MSDeformAttnFusedFunction.apply(leaves_b[0].masked_fill(mask[..., None, None], 0.0), shapes, lsi,
+                                            leaves_b[1], leaves_b[2], leaves_b[3])
+    out_b.backward(go)
+
+    assert torch.equal(out_a, out_b)                       # same products in the same order: bit-identical
+    assert leaves_a[0].grad[mask].abs().max() == 0
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for a, b, what in zip(leaves_a, leaves_b, ("grad_value", "grad_offsets", "grad_logits", "grad_reference_points")):
+        a, b = a.grad.double(), b.grad.double()
+        assert (a - b).abs().max() <= tol * b.abs().max() + 1e-6, (what, float((a - b).abs().max()), float(b.abs().max()))
+    # uint8 masks are taken as they are
+    out_c = MSDeformAttnFusedFunction.apply(value, shapes, lsi, offsets, logits, ref, mask.to(torch.uint8) * 255)
+    assert torch.equal(out_c, out_a)
+
+
 @pytest.mark.parametrize("ref_dim", [2, 4])
 def test_module_fused_and_unfused_paths_agree(ref_dim):
     from ir_ads_b200 import MultiScaleDeformableAttention
@@ -190,6 +240,7 @@ def test_module_fused_and_unfused_paths_agree(ref_dim):
     ref_pts = torch.rand(B, Q, 4, ref_dim, device=DEV)
     mask = torch.zeros(B, S, dtype=torch.bool, device=DEV)
     mask[0, :5] = True
+    mask[1] = torch.rand(S, device=DEV) < 0.25            # the fused path folds the mask into the kernels
     res = {}
     for fused in (True, False):
         m.fuse_pre_ops = fused
