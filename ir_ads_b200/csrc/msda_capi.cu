@@ -175,6 +175,19 @@ bool use_tile2d(const Dims& d, unsigned flags) {
 // slack covers them, the kernel's grid-stride step covers anything else.
 int64_t tile2d_bound(const Dims& d, int rpc) { return ((int64_t)d.S + rpc - 1) / rpc * 5 / 4 + 32 * (int64_t)d.L; }
 
+// CTA sizes of the single-pass row orders (LINEAR, STRIP).  An SM re-uses a CTA's slot only when the CTA's slowest
+// warp is done, so small CTAs keep more warps busy: cfg 2 forward 0.665 / 0.635 / 0.620 ms at 256 / 128 / 64
+// threads, backward 1.687 / 1.672 / 1.695 ms (profiles/r01s_experiments.txt).  The tile orders keep their own.
+#ifndef MSDA_FWD_THREADS
+#define MSDA_FWD_THREADS 64
+#endif
+#ifndef MSDA_BWD_THREADS
+#define MSDA_BWD_THREADS 128
+#endif
+constexpr int kFwdThreads = MSDA_FWD_THREADS, kBwdThreads = MSDA_BWD_THREADS;
+constexpr int fwd_threads(int threads, int order) { return (order == 0 || order == 2) ? kFwdThreads : threads; }
+constexpr int bwd_threads(int threads, int order) { return (order == 0 || order == 2) ? kBwdThreads : threads; }
+
 // channels per lane: 8 for bf16 rows of 32+ channels (16-byte lane loads), else 4
 template <int D, typename VT>
 constexpr int cpl_of() { return (sizeof(VT) == 2 && D >= 32) ? 8 : 4; }
@@ -231,6 +244,27 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
   return MSDA_OK;
 }
 
+#ifdef MSDA_EXP_SLIM
+// Kernel-variant experiment builds (tools/variant.sh): only D = 32, P = 4, LINEAR / STRIP orders are instantiated,
+// so a variant compiles in well under a minute.  Never defined for the product library.
+#define MSDA_DISPATCH_ORDER(D_, VT_, PT_, CALL)                                      \
+  do {                                                                               \
+    if (use_strip(d, flags)) return CALL(D_, VT_, PT_, 256, 2);                      \
+    return CALL(D_, VT_, PT_, 256, 0);                                               \
+  } while (0)
+#define MSDA_DISPATCH_PT(D_, VT_, CALL)                      \
+  do {                                                       \
+    if (d.P == 4) MSDA_DISPATCH_ORDER(D_, VT_, 4, CALL);     \
+    return fail(MSDA_ERR_UNSUPPORTED, "slim build: P=%d", d.P); \
+  } while (0)
+#define MSDA_DISPATCH_D(VT_, CALL)                           \
+  do {                                                       \
+    switch (d.D) {                                           \
+      case 32: MSDA_DISPATCH_PT(32, VT_, CALL);              \
+      default: return fail(MSDA_ERR_UNSUPPORTED, "slim build: D=%d", d.D); \
+    }                                                        \
+  } while (0)
+#else
 #define MSDA_DISPATCH_ORDER(D_, VT_, PT_, CALL)                                      \
   do {                                                                               \
     if (use_tile2d(d, flags)) return CALL(D_, VT_, PT_, 256, 3);                     \
@@ -256,11 +290,12 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
       default: return fail(MSDA_ERR_UNSUPPORTED, "fast path: D=%d", d.D); \
     }                                                        \
   } while (0)
+#endif
 
 int fwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* value, const int64_t* shapes,
              const int64_t* lsi, const void* loc, const void* w, void* out) {
 #define CALL_FWD(D_, VT_, PT_, TH_, TL_)                                                              \
-  launch_fwd_fast<D_, VT_, PT_, TH_, TL_>(st, d, value, shapes, lsi, loc, w, out, msda::FusedArgs{}, \
+  launch_fwd_fast<D_, VT_, PT_, fwd_threads(TH_, TL_), TL_>(st, d, value, shapes, lsi, loc, w, out, msda::FusedArgs{}, \
                                           (flags & MSDA_FLAG_STRIP_HEAD_MAJOR) ? 1 : 0)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_FWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_FWD);
@@ -274,7 +309,7 @@ int bwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const vo
   // on the crossbar-bound kernel); the forward keeps LINEAR
   if (!(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED | MSDA_FLAG_ORDER_TILE2D))) flags |= MSDA_FLAG_ORDER_STRIP;
 #define CALL_BWD(D_, VT_, PT_, TH_, TL_) \
-  launch_bwd_fast<D_, VT_, PT_, TH_, TL_, float>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw, nullptr, \
+  launch_bwd_fast<D_, VT_, PT_, bwd_threads(TH_, TL_), TL_, float>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw, nullptr, \
                                                  msda::FusedArgs{}, coarse_budget,                                \
                                                  (flags & MSDA_FLAG_STRIP_HEAD_MAJOR) ? 1 : 0)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
@@ -407,7 +442,7 @@ int bwd_fast_det(cudaStream_t st, const Dims& d, int dtype, const void* go, cons
                  const msda::DetScale* det) {
   const unsigned flags = MSDA_FLAG_ORDER_LINEAR;
 #define CALL_BWD(D_, VT_, PT_, TH_, TL_)                                                                      \
-  launch_bwd_fast<D_, VT_, PT_, 256, 0, unsigned long long>(st, d, go, value, shapes, lsi, loc, w, acc, gl, \
+  launch_bwd_fast<D_, VT_, PT_, kBwdThreads, 0, unsigned long long>(st, d, go, value, shapes, lsi, loc, w, acc, gl, \
                                                                 gw, det)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
@@ -419,7 +454,7 @@ int bwd_fast_noscatter(cudaStream_t st, const Dims& d, int dtype, const void* go
                        const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, void* gl, void* gw) {
   const unsigned flags = MSDA_FLAG_ORDER_LINEAR;
 #define CALL_BWD(D_, VT_, PT_, TH_, TL_)                                                                       \
-  launch_bwd_fast<D_, VT_, PT_, 256, 0, msda::NoScatter>(st, d, go, value, shapes, lsi, loc, w,                  \
+  launch_bwd_fast<D_, VT_, PT_, kBwdThreads, 0, msda::NoScatter>(st, d, go, value, shapes, lsi, loc, w,                  \
                                                          (msda::NoScatter*)nullptr, gl, gw, nullptr)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
@@ -485,6 +520,9 @@ bool det_sorted_ok(const Dims& d, int dtype, unsigned flags) {
     if (d.P == 8) return CALL(D_, VT_, 8);        \
     return CALL(D_, VT_, 0);                      \
   } while (0)
+#ifdef MSDA_EXP_SLIM
+#define MSDA_DISPATCH_D_FUSED(VT_, CALL) return fail(MSDA_ERR_UNSUPPORTED, "slim build: no fused kernels")
+#else
 #define MSDA_DISPATCH_D_FUSED(VT_, CALL)                     \
   do {                                                       \
     switch (d.D) {                                           \
@@ -495,10 +533,11 @@ bool det_sorted_ok(const Dims& d, int dtype, unsigned flags) {
       default: return fail(MSDA_ERR_UNSUPPORTED, "fused path: D=%d", d.D); \
     }                                                        \
   } while (0)
+#endif
 
 int fwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
               const void* off, const void* logits, void* out, msda::FusedArgs fa) {
-#define CALL_FF(D_, VT_, PT_) launch_fwd_fast<D_, VT_, PT_, 256, 0, msda::kPreFused>(st, d, value, shapes, lsi, off, logits, out, fa)
+#define CALL_FF(D_, VT_, PT_) launch_fwd_fast<D_, VT_, PT_, kFwdThreads, 0, msda::kPreFused>(st, d, value, shapes, lsi, off, logits, out, fa)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D_FUSED(float, CALL_FF);
   MSDA_DISPATCH_D_FUSED(__nv_bfloat16, CALL_FF);
 #undef CALL_FF
@@ -508,7 +547,7 @@ int bwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* go, const v
               const int64_t* lsi, const void* off, const void* logits, float* gv, void* goff, void* glog,
               msda::FusedArgs fa) {
 #define CALL_FB(D_, VT_, PT_)                                                                                    \
-  launch_bwd_fast<D_, VT_, PT_, 256, 2, float, msda::kPreFused>(st, d, go, value, shapes, lsi, off, logits, gv, goff, glog, \
+  launch_bwd_fast<D_, VT_, PT_, kBwdThreads, 2, float, msda::kPreFused>(st, d, go, value, shapes, lsi, off, logits, gv, goff, glog, \
                                                      nullptr, fa)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D_FUSED(float, CALL_FB);
   MSDA_DISPATCH_D_FUSED(__nv_bfloat16, CALL_FB);
@@ -516,6 +555,9 @@ int bwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* go, const v
 }
 
 // DCNv3: runtime point count (K = kernel_h * kernel_w), LINEAR forward, STRIP backward
+#ifdef MSDA_EXP_SLIM
+#define MSDA_DISPATCH_D_DCN(VT_, CALL) return fail(MSDA_ERR_UNSUPPORTED, "slim build: no DCNv3 kernels")
+#else
 #define MSDA_DISPATCH_D_DCN(VT_, CALL)                       \
   do {                                                       \
     switch (d.D) {                                           \
@@ -526,11 +568,12 @@ int bwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* go, const v
       default: return fail(MSDA_ERR_UNSUPPORTED, "dcnv3: group_channels=%d", d.D); \
     }                                                        \
   } while (0)
+#endif
 
 int fwd_dcn(cudaStream_t st, const Dims& d, int dtype, const void* input, const void* off, const void* mask, void* out,
             msda::FusedArgs fa) {
 #define CALL_DF(D_, VT_) \
-  launch_fwd_fast<D_, VT_, 0, 256, 0, msda::kPreDcn>(st, d, input, nullptr, nullptr, off, mask, out, fa)
+  launch_fwd_fast<D_, VT_, 0, kFwdThreads, 0, msda::kPreDcn>(st, d, input, nullptr, nullptr, off, mask, out, fa)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D_DCN(float, CALL_DF);
   MSDA_DISPATCH_D_DCN(__nv_bfloat16, CALL_DF);
 #undef CALL_DF
@@ -539,7 +582,7 @@ int fwd_dcn(cudaStream_t st, const Dims& d, int dtype, const void* input, const 
 int bwd_dcn(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* input, const void* off,
             const void* mask, float* gi, void* goff, void* gmask, msda::FusedArgs fa) {
 #define CALL_DB(D_, VT_)                                                                                          \
-  launch_bwd_fast<D_, VT_, 0, 256, 2, float, msda::kPreDcn>(st, d, go, input, nullptr, nullptr, off, mask, gi, goff, \
+  launch_bwd_fast<D_, VT_, 0, kBwdThreads, 2, float, msda::kPreDcn>(st, d, go, input, nullptr, nullptr, off, mask, gi, goff, \
                                                             gmask, nullptr, fa)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D_DCN(float, CALL_DB);
   MSDA_DISPATCH_D_DCN(__nv_bfloat16, CALL_DB);

@@ -187,6 +187,16 @@ __device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes
   __syncthreads();
 }
 
+// LINEAR / STRIP orders need no tile table: one barrier, no serial section (first_coarse is left to the caller)
+__device__ __forceinline__ void load_levels_plain(LevelTab* tab, const int64_t* shapes, const int64_t* lsi, int L) {
+  if (threadIdx.x < L) {
+    tab->H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+    tab->W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+    tab->start[threadIdx.x] = (int)lsi[threadIdx.x];
+  }
+  __syncthreads();
+}
+
 // DCNv3: a single level whose shape comes with the call, not from device tensors
 template <int TW, int TH>
 __device__ __forceinline__ void set_single_level(LevelTab* tab, int H, int W) {
@@ -215,7 +225,7 @@ template <int D, int THREADS>
 struct Geom {
   static constexpr int LANES = D / 4;
   static constexpr int RPC = THREADS / LANES;                 // rows per CTA pass
-  static constexpr int TW = (RPC >= 128) ? 16 : ((RPC >= 32) ? 8 : 4);
+  static constexpr int TW = (RPC >= 128) ? 16 : ((RPC >= 32) ? 8 : ((RPC >= 4) ? 4 : RPC));   // tile orders only
   static constexpr int TH = RPC / TW;
   static_assert(TW * TH == RPC, "tile must cover the CTA's rows");
 };
@@ -274,6 +284,8 @@ struct RowWalk {
   int64_t item, n_items, rows;
   int rin, BH;
   bool head_major = false;   // STRIP only: items ordered (image, head, strip) instead of (image, strip, head)
+  __device__ __forceinline__ RowWalk() {}
+  // LINEAR / STRIP do not read `tab`, so they may start before the level table is loaded
   __device__ __forceinline__ RowWalk(const LevelTab* tab, int B, int H, int64_t rows_) : rows(rows_) {
     rin = threadIdx.x / G::LANES;
     item = blockIdx.x;
@@ -527,7 +539,7 @@ template <int D, typename VT, int PT, int THREADS, int ORDER, int PRE, int CPL>
 #ifndef MSDA_FWD_MINB
 #define MSDA_FWD_MINB 6
 #endif
-__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_FWD_MINB : ((THREADS == 512) ? 3 : 1))
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256) ? MSDA_FWD_MINB * (256 / THREADS) : ((THREADS == 512) ? 3 : 1))
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ w, VT* __restrict__ out, const FusedArgs fused, int B, int S, int H,
@@ -546,9 +558,6 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   const int NP = L * P;
   const int row_words = fwd_row_words(NP, STAGED);
 
-  if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
-  else load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
-
   const int sub = (threadIdx.x & 31) % LANES;            // lane inside the row
   const int rin = threadIdx.x / LANES;                   // row inside the CTA
   const int HD = H * D;
@@ -558,10 +567,37 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   float2* raw_xy = reinterpret_cast<float2*>(my + ((5 * NP + 1) & ~1));
   float* raw_w = my + ((5 * NP + 1) & ~1) + 2 * NP;
 
-  RowWalk<DL, THREADS, ORDER> walk(tab, B, H, rows);
-  walk.head_major = head_major != 0;
-  if (walk.done()) return;
-  RowRef cur = walk.get(tab, L, H, Q);
+  // Single-pass orders (LINEAR, STRIP) know their row without the level table, so the first locations / weights
+  // of the row are requested BEFORE the table's load + barrier: the two global-memory latencies of a CTA's
+  // start-up overlap instead of adding up.
+  constexpr bool EARLY = (ORDER == 0 || ORDER == 2) && PRE == kPrePlain;
+  constexpr int kEarly = 2;                              // row-loop iterations whose loads are issued early
+  float2 early_xy[kEarly];
+  float early_w[kEarly];
+  RowWalk<DL, THREADS, ORDER> walk;
+  RowRef cur;
+  if constexpr (EARLY) {
+    walk = RowWalk<DL, THREADS, ORDER>(tab, B, H, rows);
+    walk.head_major = head_major != 0;
+    if (walk.done()) return;                             // uniform over the CTA
+    cur = walk.get(tab, L, H, Q);
+#pragma unroll
+    for (int i = 0; i < kEarly; ++i) {
+      const int pt = sub + i * LANES;
+      const bool on = cur.live && pt < NP;
+      early_xy[i] = on ? __ldg(reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2) + pt) : make_float2(0.f, 0.f);
+      early_w[i] = on ? __ldg(w + cur.row * (int64_t)NP + pt) : 0.0f;
+    }
+    load_levels_plain(tab, shapes, lsi, L);
+  } else {
+    if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
+    else if constexpr (ORDER == 0 || ORDER == 2) load_levels_plain(tab, shapes, lsi, L);
+    else load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
+    walk = RowWalk<DL, THREADS, ORDER>(tab, B, H, rows);
+    walk.head_major = head_major != 0;
+    if (walk.done()) return;
+    cur = walk.get(tab, L, H, Q);
+  }
   if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
   while (true) {
     bool has_next = false;
@@ -582,15 +618,12 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       if constexpr (FUSED) sm_sum = row_softmax<LANES, 1>(wp, reinterpret_cast<float*>(s_oc), NP, sub);
       if (cur.live) {
         const float* rp = FUSED ? fused.ref + (cur.row / H) * (int64_t)L * fused.ref_dim : nullptr;
-        for (int pt = sub; pt < NP; pt += LANES) {
-          float2 xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
-          float aw;
+        // one record from a point's raw location / weight (FUSED: raw offset; the weight comes from the softmax)
+        auto build = [&](int pt, float2 xy, float aw) {
           const int l = level_of<PT>(pt, P);
           if constexpr (FUSED) {
             aw = __fdiv_rn(__int_as_float(s_oc[pt]), sm_sum);
             xy = fused_location(xy, rp + l * fused.ref_dim, fused.ref_dim, tab->H[l], tab->W[l], fused.inv_P);
-          } else {
-            aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
           }
           PointRec r;
           if constexpr (DCN) {
@@ -604,7 +637,15 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
           }
           s_cw[pt] = r.cw;
           s_oc[pt] = r.oc;
+        };
+        int pt = sub;
+        if constexpr (EARLY) {   // the loads of these iterations were issued before the level table's barrier
+#pragma unroll
+          for (int i = 0; i < kEarly; ++i, pt += LANES)
+            if (pt < NP) build(pt, early_xy[i], early_w[i]);
         }
+        for (; pt < NP; pt += LANES)
+          build(pt, STAGED ? raw_xy[pt] : __ldg(lp + pt), (STAGED && !FUSED) ? raw_w[pt] : (FUSED ? 0.0f : __ldg(wp + pt)));
       }
     }
     __syncwarp();
@@ -768,7 +809,7 @@ __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
 #define MSDA_BWD_MINB 4
 #endif
 template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC, int PRE, int CPL>
-__global__ void __launch_bounds__(THREADS, (THREADS == 256) ? MSDA_BWD_MINB : 1)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256) ? MSDA_BWD_MINB * (256 / THREADS) : 1)
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ w,
@@ -791,10 +832,6 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   const int NP = L * P;
   const int row_words = bwd_row_words(NP, STAGED);
 
-  if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
-  else load_levels<G::TW, G::TH>(tab, shapes, lsi, L, D, coarse_budget);
-  const int red_points = tab->first_coarse * P;   // points [0, red_points) scatter with reds here
-
   const int sub = (threadIdx.x & 31) % LANES;
   const int rin = threadIdx.x / LANES;
   const int HD = H * D;
@@ -806,14 +843,48 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   const float gscale = det ? det->scale : 1.0f;
 
+  // Single-pass orders know their row without the level table: the row's grad_out and its first locations /
+  // weights are requested before the table's load + barrier (see the forward kernel).
+  constexpr bool EARLY = (ORDER == 0 || ORDER == 2) && PRE == kPrePlain;
+  constexpr int kEarly = 2;
+  float2 early_xy[kEarly];
+  float early_w[kEarly];
   // A warp stays converged for the full-mask shuffles below: rows that do not exist (edge tiles,
   // the tail of the last CTA) get all-zero weights, so they scatter nothing and never write.
-  RowWalk<DL, THREADS, ORDER> walk(tab, B, H, rows);
-  walk.head_major = head_major != 0;
-  if (walk.done()) return;
-  RowRef cur = walk.get(tab, L, H, Q);
-  if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
+  RowWalk<DL, THREADS, ORDER> walk;
+  RowRef cur;
   Vec<CPL> go = vzero<CPL>();
+  if constexpr (EARLY) {
+    walk = RowWalk<DL, THREADS, ORDER>(tab, B, H, rows);
+    walk.head_major = head_major != 0;
+    if (walk.done()) return;                             // uniform over the CTA
+    cur = walk.get(tab, L, H, Q);
+    if (cur.live) go = ldv<CPL>(grad_out + cur.row * D + sub * CPL);
+#pragma unroll
+    for (int i = 0; i < kEarly; ++i) {
+      const int pt = sub + i * LANES;
+      const bool on = cur.live && pt < NP;
+      early_xy[i] = on ? __ldg(reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2) + pt) : make_float2(0.f, 0.f);
+      early_w[i] = on ? __ldg(w + cur.row * (int64_t)NP + pt) : 0.0f;
+    }
+    load_levels_plain(tab, shapes, lsi, L);
+  } else {
+    if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
+    else if constexpr (ORDER == 0 || ORDER == 2) load_levels_plain(tab, shapes, lsi, L);
+    else load_levels<G::TW, G::TH>(tab, shapes, lsi, L, D, coarse_budget);
+    walk = RowWalk<DL, THREADS, ORDER>(tab, B, H, rows);
+    walk.head_major = head_major != 0;
+    if (walk.done()) return;
+    cur = walk.get(tab, L, H, Q);
+  }
+  // points [0, red_points) scatter with reds here; the rest belongs to msda_bwd_coarse_kernel (opt-in)
+  int first_coarse = L;
+  if (!DCN && coarse_budget > 0) {
+    if constexpr (ORDER == 0 || ORDER == 2) first_coarse = coarse_first_level(tab->H, tab->W, L, D, coarse_budget);
+    else first_coarse = tab->first_coarse;
+  }
+  const int red_points = first_coarse * P;
+  if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
   if (STAGED && cur.live) go = ldv<CPL>(grad_out + cur.row * D + sub * CPL);
   while (true) {
     bool has_next = false;
@@ -824,7 +895,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
       if (has_next) nxt = walk.get(tab, L, H, Q);
       cp_async_wait_all();
       __syncwarp();
-    } else {
+    } else if constexpr (!EARLY) {
       go = cur.live ? ldv<CPL>(grad_out + cur.row * D + sub * CPL) : vzero<CPL>();
     }
     const float* rp = FUSED ? fused.ref + (cur.row / H) * (int64_t)L * fused.ref_dim : nullptr;
@@ -833,18 +904,16 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
       const float* wp = w + cur.row * (int64_t)NP;
       float sm_sum = 1.0f;
       if constexpr (FUSED) sm_sum = row_softmax<LANES, 4>(wp, reinterpret_cast<float*>(s_fin) + 3, NP, sub);
-      for (int pt = sub; pt < NP; pt += LANES) {
+      // one record from a point's raw location / weight (FUSED: raw offset; the weight comes from the softmax);
+      // rows that do not exist get all-zero records
+      auto build = [&](int pt, float2 xy, float aw) {
         float4 cw = zero;
         int4 fin = make_int4(0, __float_as_int(-1.0f), 0, 0);
         if (cur.live) {
-          float2 xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
-          float aw;
           const int l = level_of<PT>(pt, P);
           if constexpr (FUSED) {
             aw = __fdiv_rn(__int_as_float(s_fin[pt].w), sm_sum);
             xy = fused_location(xy, rp + l * fused.ref_dim, fused.ref_dim, tab->H[l], tab->W[l], fused.inv_P);
-          } else {
-            aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
           }
           PointRec r;
           if constexpr (DCN) {
@@ -861,6 +930,21 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         }
         s_cw[pt] = cw;
         s_fin[pt] = fin;
+      };
+      int pt = sub;
+      if constexpr (EARLY) {   // the loads of these iterations were issued before the level table's barrier
+#pragma unroll
+        for (int i = 0; i < kEarly; ++i, pt += LANES)
+          if (pt < NP) build(pt, early_xy[i], early_w[i]);
+      }
+      for (; pt < NP; pt += LANES) {
+        float2 xy = make_float2(0.f, 0.f);
+        float aw = 0.0f;
+        if (cur.live) {
+          xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
+          if constexpr (!FUSED) aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
+        }
+        build(pt, xy, aw);
       }
     }
     __syncwarp();
