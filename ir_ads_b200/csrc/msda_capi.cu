@@ -255,6 +255,7 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
 #define MSDA_DISPATCH_PT(D_, VT_, CALL)                      \
   do {                                                       \
     if (d.P == 4) MSDA_DISPATCH_ORDER(D_, VT_, 4, CALL);     \
+    if (d.P == 8) MSDA_DISPATCH_ORDER(D_, VT_, 8, CALL);     \
     return fail(MSDA_ERR_UNSUPPORTED, "slim build: P=%d", d.P); \
   } while (0)
 #define MSDA_DISPATCH_D(VT_, CALL)                           \
@@ -484,13 +485,41 @@ int det_gather(cudaStream_t st, const Dims& d, const void* go, const int4* entri
   return MSDA_OK;
 }
 
+// dense problems reduce per cell (one pass over the entries), sparse ones gather per pixel (msda_det.cuh)
+bool det_dense(const Dims& d) { return d.n_points() >= (int64_t)msda::kDetDenseRatio * d.B * d.S * d.H; }
+
+template <typename VT>
+int det_cell_reduce(cudaStream_t st, const Dims& d, const void* go, const int4* entries, const int* bin_start,
+                    int64_t n_bins, const int64_t* shapes, const int64_t* lsi, const msda::DetScale* scale,
+                    unsigned long long* acc) {
+  const int64_t slices = (d.n_points() + msda::kDetSlice - 1) / msda::kDetSlice;   // upper bound: gated points have no entry
+#define CALL_G(D_)                                                                                            \
+  do {                                                                                                        \
+    constexpr int GPC = 256 / (D_ / 4);                                                                       \
+    msda::det_cell_reduce_kernel<D_, VT><<<(unsigned)((slices + GPC - 1) / GPC), 256, 0, st>>>(               \
+        (const VT*)go, entries, bin_start, (int)n_bins, shapes, lsi, scale, acc, d.S, d.H, d.L);              \
+  } while (0)
+  switch (d.D) {
+    case 16: CALL_G(16); break;
+    case 32: CALL_G(32); break;
+    case 64: CALL_G(64); break;
+    case 128: CALL_G(128); break;
+    default: return fail(MSDA_ERR_UNSUPPORTED, "det cell reduce: D=%d", d.D);
+  }
+#undef CALL_G
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MSDA_CUDA(cudaGetLastError());
+  return MSDA_OK;
+}
+
 // Workspace of the sorted deterministic path (all 16-byte aligned):
 //   [bins+1 ints: counts -> starts][bins ints: cursors][scan block sums][entries: n_points x 16 B][amax x2, DetScale]
+//   [fixed-point accumulators: n_value x 8 B]
 struct DetLayout {
   int64_t bins;        // upper bound, B*H*(2S+2L)
   int64_t n_scan;      // bins + 1
   int64_t scan_blocks;
-  size_t off_cursor, off_sums, off_entries, off_misc, total;
+  size_t off_cursor, off_sums, off_entries, off_misc, off_acc, total;
 };
 DetLayout det_layout(const Dims& d) {
   DetLayout l;
@@ -502,7 +531,8 @@ DetLayout det_layout(const Dims& d) {
   l.off_sums = l.off_cursor + up((size_t)l.bins * 4);
   l.off_entries = l.off_sums + up((size_t)l.scan_blocks * 4);
   l.off_misc = l.off_entries + up((size_t)d.n_points() * 16);
-  l.total = l.off_misc + 256;
+  l.off_acc = l.off_misc + 256;
+  l.total = l.off_acc + (det_dense(d) ? up((size_t)d.n_value() * 8) : 0);   // accumulators: cell reduce only
   return l;
 }
 // the sorted path needs 32-bit bin / entry / row indices
@@ -760,12 +790,12 @@ int msda_backward_hs(void* stream, const void* grad_output, const void* value, c
     const bool sorted = det_sorted_ok(d, dtype, flags);
     const DetLayout lay = sorted ? det_layout(d) : DetLayout{};
     char* ws = static_cast<char*>(workspace);
-    auto* acc = static_cast<unsigned long long*>(workspace);
+    auto* acc = reinterpret_cast<unsigned long long*>(ws + (sorted ? lay.off_acc : 0));
     auto* amax = reinterpret_cast<unsigned*>(ws + (sorted ? lay.off_misc : (size_t)nv * 8));
     auto* scale = reinterpret_cast<msda::DetScale*>(reinterpret_cast<char*>(amax) + 16);
-    if (sorted) {   // zero the bins, cursors and {amax, scale}; entries are fully overwritten
+    if (sorted) {   // zero the bins, cursors, {amax, scale} and the accumulators; entries are fully overwritten
       MSDA_CUDA(cudaMemsetAsync(ws, 0, lay.off_sums, st));
-      MSDA_CUDA(cudaMemsetAsync(ws + lay.off_misc, 0, 256, st));
+      MSDA_CUDA(cudaMemsetAsync(ws + lay.off_misc, 0, lay.total - lay.off_misc, st));
     } else {
       MSDA_CUDA(cudaMemsetAsync(workspace, 0, need, st));
     }
@@ -805,10 +835,26 @@ int msda_backward_hs(void* stream, const void* grad_output, const void* value, c
       if (int s2 = bwd_fast_noscatter(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
                                       attn_weight, grad_sampling_loc, grad_attn_weight))
         return s2;
+      if (!det_dense(d)) {
+        if (dtype == MSDA_F32)
+          return det_gather<float>(st, d, grad_output, entries, bins, spatial_shapes, level_start_index, scale, grad_value);
+        return det_gather<__nv_bfloat16>(st, d, grad_output, entries, bins, spatial_shapes, level_start_index, scale,
+                                         grad_value);
+      }
+      int s3;
       if (dtype == MSDA_F32)
-        return det_gather<float>(st, d, grad_output, entries, bins, spatial_shapes, level_start_index, scale, grad_value);
-      return det_gather<__nv_bfloat16>(st, d, grad_output, entries, bins, spatial_shapes, level_start_index, scale,
-                                       grad_value);
+        s3 = det_cell_reduce<float>(st, d, grad_output, entries, bins, lay.bins, spatial_shapes, level_start_index, scale, acc);
+      else
+        s3 = det_cell_reduce<__nv_bfloat16>(st, d, grad_output, entries, bins, lay.bins, spatial_shapes, level_start_index,
+                                            scale, acc);
+      if (s3 != MSDA_OK) return s3;
+      const int g_fin = grid_for(nv, 256, 148 * 16);
+      const long long* sacc = reinterpret_cast<const long long*>(acc);
+      if (dtype == MSDA_F32) msda::msda_det_finalize_kernel<float><<<g_fin, 256, 0, st>>>(sacc, (float*)grad_value, nv, scale);
+      else msda::msda_det_finalize_kernel<__nv_bfloat16><<<g_fin, 256, 0, st>>>(sacc, (__nv_bfloat16*)grad_value, nv, scale);
+      count();
+      MSDA_CUDA(cudaGetLastError());
+      return MSDA_OK;
     }
     int s;
     if (fast_ok(d, dtype, flags))

@@ -6,9 +6,14 @@
 //                             kernels) and counts itself in that cell's bin
 //   2. scan (3 small kernels) bin counts -> bin start offsets
 //   3. det_bin_kernel<true>   every point writes a 16-byte entry {row, lw, lh, attention weight} into its bin
-//   4. det_gather_kernel      one lane group per (image, pixel, head): walks the (up to) four bins whose
-//                             cells have this pixel as a corner, gathers grad_out rows and accumulates in
-//                             64-bit fixed point IN REGISTERS, writes the pixel's D channels once.
+//   4a. det_gather_kernel     (sparse problems: fewer than kDetDenseRatio points per pixel and head, e.g. decoder
+//                             cross-attention) one lane group per (image, pixel, head): walks the (up to) four
+//                             bins whose cells have this pixel as a corner, gathers grad_out rows and accumulates
+//                             in 64-bit fixed point IN REGISTERS, writes the pixel's D channels once.
+//   4b. det_cell_reduce_kernel (dense problems, e.g. encoder self-attention) one lane group per slice of 64
+//                             consecutive entries: every entry is read once, the four corner sums of a cell are
+//                             kept in registers and handed to a fixed-point accumulation buffer with 64-bit
+//                             integer reds when the cell changes; msda_det_finalize_kernel converts.
 // Bins are filled in arbitrary order (an atomic cursor), but integer accumulation is order independent,
 // so the result is bit-reproducible -- and bit-identical to the fixed-point reds of the generic
 // deterministic path (same products, same scale).  No atomics touch grad_value, no zero-fill is needed.
@@ -50,6 +55,10 @@ __device__ __forceinline__ void load_cell_tab(CellTab* t, const int64_t* shapes,
   }
   __syncthreads();
 }
+
+// dense problems (points per pixel and head >= this) take the cell reduce, sparse ones the per-pixel gather:
+// cfg 3 (1.4 points per pixel-head) 0.60 vs 0.81 ms, cfg 2 (16) 3.31 vs 3.02 ms, cfg 5 (39) 8.26 vs 5.65 ms
+constexpr int kDetDenseRatio = 4;
 
 // upper bound of bins per (image, head) that needs only S and L: (H+1)(W+1) <= 2HW + 2
 __host__ __device__ constexpr int64_t det_cells_bound(int64_t S, int64_t L) { return 2 * S + 2 * L; }
@@ -206,6 +215,123 @@ det_gather_kernel(const VT* __restrict__ grad_out, const int4* __restrict__ entr
   const float4 r = make_float4((float)((double)a0 * inv), (float)((double)a1 * inv), (float)((double)a2 * inv),
                                (float)((double)a3 * inv));
   st4(grad_value + ((b * S + s) * H + h) * (int64_t)D + sub * 4, r);
+}
+
+// ---- cell reduce: one pass over the sorted entries ---------------------------------------------------------
+// The per-pixel gather above visits every entry four times (once per corner pixel) and gives a coarse pixel's
+// hundreds of entries to ONE lane group.  Here the entry array is cut into slices of kDetSlice consecutive
+// entries; one LANES-wide lane group walks a slice, keeps the four corner sums of the current cell in 64-bit
+// fixed point in registers (16 accumulators per lane) and, whenever the cell changes, adds them to the fixed-point
+// accumulation buffer [B, S, H, D] with 64-bit integer reds.  Work per group is bounded whatever the
+// entries-per-cell distribution is, every entry (and its grad_out row) is read once, and the number of reds is
+// ~(cells + slices) x 4 instead of points x 4.  Integer addition commutes, so the result is bit-identical to the
+// gather's and to the fixed-point red path's (same products, same scale); msda_det_finalize_kernel converts.
+// Lane `sub` owns channels {sub, LANES+sub, 2*LANES+sub, 3*LANES+sub}: the lanes of a group then write
+// 8*LANES contiguous bytes per red instruction (full 32-byte sectors; there is no vector form of the 64-bit red).
+constexpr int kDetSlice = 64;   // measured at cfg 2 / cfg 5: 32 -> 3.44 / 6.36 ms, 64 -> 3.02 / 5.65 ms, 128 -> 3.33 / 6.05 ms
+
+__device__ __forceinline__ float det_ld(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float det_ld(const __nv_bfloat16* p) {
+  return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+
+template <int D, typename VT>
+__global__ void __launch_bounds__(256)
+det_cell_reduce_kernel(const VT* __restrict__ grad_out, const int4* __restrict__ entries,
+                       const int* __restrict__ bin_start, int n_bins, const int64_t* __restrict__ shapes,
+                       const int64_t* __restrict__ lsi, const DetScale* __restrict__ det,
+                       unsigned long long* __restrict__ acc, int S, int H, int L) {
+  constexpr int LANES = D / 4;
+  constexpr int GPC = 256 / LANES;   // lane groups per CTA
+  __shared__ CellTab tab;
+  load_cell_tab(&tab, shapes, lsi, L);
+  const int sub = (threadIdx.x & 31) % LANES;
+  const int total = __ldg(bin_start + n_bins);                       // entries actually written (gated-out points have none)
+  const int64_t slice = (int64_t)blockIdx.x * GPC + threadIdx.x / LANES;
+  if (slice * kDetSlice >= total) return;
+  const int e_begin = (int)(slice * kDetSlice);
+  const int e_end = min(e_begin + kDetSlice, total);
+  const float scale = det->scale;
+
+  // the (non-empty) bin that holds entry e: the last bin whose start is <= e
+  auto find_bin = [&](int e, int lo) {
+    int hi = n_bins;                                                 // bin_start[n_bins] == total > e
+    while (hi - lo > 1) {
+      const int mid = lo + ((hi - lo) >> 1);
+      if (__ldg(bin_start + mid) <= e) lo = mid;
+      else hi = mid;
+    }
+    return lo;
+  };
+  long long a[4][4];
+  auto clear = [&] {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[k][i] = 0;
+  };
+  // add the four corner sums of cell `bin` to the accumulation buffer (corners outside the map are dropped)
+  auto flush = [&](int bin) {
+    const int bh = bin / tab.cells_per_bh, rem = bin - bh * tab.cells_per_bh;
+    int l = 0;
+    for (int k = 1; k < L; ++k)
+      if (rem >= tab.cell_begin[k]) l = k;
+    const int Wl = tab.W[l], Hl = tab.H[l], W1 = Wl + 1;
+    const int local = rem - tab.cell_begin[l];
+    const int cy = local / W1, y0 = cy - 1, x0 = local - cy * W1 - 1;
+    const int b = bh / H, h = bh - b * H;
+    unsigned long long* base = acc + ((int64_t)b * S * H + h) * D + sub;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = y0 + (k >> 1), xx = x0 + (k & 1);
+      if (yy >= 0 && yy < Hl && xx >= 0 && xx < Wl) {
+        unsigned long long* p = base + (int64_t)(tab.start[l] + yy * Wl + xx) * H * D;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (a[k][i] != 0) atomicAdd(p + i * LANES, (unsigned long long)a[k][i]);
+      }
+    }
+  };
+  auto load_go = [&](int row, float (&g)[4]) {
+    const VT* r = grad_out + (int64_t)row * D + sub;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = det_ld(r + i * LANES);
+  };
+
+  int bin = find_bin(e_begin, 0);
+  int bin_end = __ldg(bin_start + bin + 1);
+  clear();
+  // software pipeline: entry e+2 and the grad_out row of entry e+1 are in flight while entry e is accumulated
+  int4 ent = __ldg(entries + e_begin);
+  int4 ent1 = (e_begin + 1 < e_end) ? __ldg(entries + e_begin + 1) : ent;
+  float g[4], g1[4];
+  load_go(ent.x, g);
+  for (int e = e_begin; e < e_end; ++e) {
+    const int4 ent2 = (e + 2 < e_end) ? __ldg(entries + e + 2) : ent1;
+    if (e + 1 < e_end) load_go(ent1.x, g1);
+    if (e >= bin_end) {                                              // the cell changes: hand its sums over
+      flush(bin);
+      clear();
+      ++bin;
+      bin_end = __ldg(bin_start + bin + 1);
+      if (e >= bin_end) {                                            // a run of empty cells: search instead of walking
+        bin = find_bin(e, bin);
+        bin_end = __ldg(bin_start + bin + 1);
+      }
+    }
+    const float lw = __int_as_float(ent.y), lh = __int_as_float(ent.z), aw = __int_as_float(ent.w);
+    const float hh = 1.0f - lh, hw = 1.0f - lw;
+    const float c[4] = {hh * hw * aw, hh * lw * aw, lh * hw * aw, lh * lw * aw};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[k][i] += __float2ll_rn((c[k] * g[i]) * scale);
+    ent = ent1;
+    ent1 = ent2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = g1[i];
+  }
+  flush(bin);
 }
 
 }  // namespace msda

@@ -307,13 +307,15 @@ def test_deterministic_backward_is_bit_reproducible(dtype, D):
     assert_close(fast[1], rgv, tol, 1e-6, "atomic grad_value vs oracle")
 
 
-@pytest.mark.parametrize("cfg", ["enc", "dec"])
+@pytest.mark.parametrize("cfg", ["enc", "dec", "dec_sparse"])
 def test_deterministic_sorted_path_on_pyramids(cfg):
     """Sorted path on multi-level pyramids (encoder and decoder forms, edge locations included): bit-equal to
-    the fixed-point red path, reproducible, and within tolerance of the oracle."""
+    the fixed-point red path, reproducible, and within tolerance of the oracle.  "enc" and "dec" are dense
+    (>= 4 points per pixel and head: one-pass cell reduce), "dec_sparse" takes the per-pixel gather."""
     _, _lib, _, workloads, msda_c, _ = _mods()
     levels = [(21, 37), (11, 19), (6, 10), (3, 5)]
-    kind, Q, dist = ("encoder", 0, "model") if cfg == "enc" else ("decoder", 333, "edge")
+    kind, Q, dist = {"enc": ("encoder", 0, "model"), "dec": ("decoder", 333, "edge"),
+                     "dec_sparse": ("decoder", 40, "edge")}[cfg]
     value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, Q, 8, 32, 4, kind, dist, 17)
     go = torch.randn(2, loc.shape[1], 256, generator=torch.Generator().manual_seed(5))
     a = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_DETERMINISTIC)
