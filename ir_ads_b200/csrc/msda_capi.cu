@@ -245,7 +245,7 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
 }
 
 #ifdef MSDA_EXP_SLIM
-// Kernel-variant experiment builds (tools/variant.sh): only D = 32, P = 4, LINEAR / STRIP orders are instantiated,
+// Kernel-variant experiment builds (tools/build_variant.sh): only D = 32, P in {4, 8}, LINEAR / STRIP orders are instantiated,
 // so a variant compiles in well under a minute.  Never defined for the product library.
 #define MSDA_DISPATCH_ORDER(D_, VT_, PT_, CALL)                                      \
   do {                                                                               \

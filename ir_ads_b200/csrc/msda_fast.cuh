@@ -570,10 +570,12 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   // Single-pass orders (LINEAR, STRIP) know their row without the level table, so the first locations / weights
   // of the row are requested BEFORE the table's load + barrier: the two global-memory latencies of a CTA's
   // start-up overlap instead of adding up.
-  constexpr bool EARLY = (ORDER == 0 || ORDER == 2) && PRE == kPrePlain;
+  // (FUSED: the raw offsets are requested and the row's softmax is done before the barrier.)
+  constexpr bool EARLY = (ORDER == 0 || ORDER == 2) && PRE != kPreDcn;
   constexpr int kEarly = 2;                              // row-loop iterations whose loads are issued early
   float2 early_xy[kEarly];
   float early_w[kEarly];
+  float early_sum = 1.0f;                                // FUSED: softmax denominator of the row
   RowWalk<DL, THREADS, ORDER> walk;
   RowRef cur;
   if constexpr (EARLY) {
@@ -586,8 +588,10 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       const int pt = sub + i * LANES;
       const bool on = cur.live && pt < NP;
       early_xy[i] = on ? __ldg(reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2) + pt) : make_float2(0.f, 0.f);
-      early_w[i] = on ? __ldg(w + cur.row * (int64_t)NP + pt) : 0.0f;
+      early_w[i] = (on && !FUSED) ? __ldg(w + cur.row * (int64_t)NP + pt) : 0.0f;
     }
+    // the softmax shuffles need the whole warp; dead rows read row 0 and simply produce nothing
+    if constexpr (FUSED) early_sum = row_softmax<LANES, 1>(w + cur.row * (int64_t)NP, reinterpret_cast<float*>(s_oc), NP, sub);
     load_levels_plain(tab, shapes, lsi, L);
   } else {
     if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
@@ -613,9 +617,8 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     {
       const float2* lp = reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2);
       const float* wp = w + cur.row * (int64_t)NP;
-      float sm_sum = 1.0f;
-      // the softmax shuffles need the whole warp; dead rows read row 0 and simply produce nothing
-      if constexpr (FUSED) sm_sum = row_softmax<LANES, 1>(wp, reinterpret_cast<float*>(s_oc), NP, sub);
+      float sm_sum = early_sum;
+      if constexpr (FUSED && !EARLY) sm_sum = row_softmax<LANES, 1>(wp, reinterpret_cast<float*>(s_oc), NP, sub);
       if (cur.live) {
         const float* rp = FUSED ? fused.ref + (cur.row / H) * (int64_t)L * fused.ref_dim : nullptr;
         // one record from a point's raw location / weight (FUSED: raw offset; the weight comes from the softmax)
@@ -845,10 +848,11 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
 
   // Single-pass orders know their row without the level table: the row's grad_out and its first locations /
   // weights are requested before the table's load + barrier (see the forward kernel).
-  constexpr bool EARLY = (ORDER == 0 || ORDER == 2) && PRE == kPrePlain;
+  constexpr bool EARLY = (ORDER == 0 || ORDER == 2) && PRE != kPreDcn;
   constexpr int kEarly = 2;
   float2 early_xy[kEarly];
   float early_w[kEarly];
+  float early_sum = 1.0f;                                // FUSED: softmax denominator of the row
   // A warp stays converged for the full-mask shuffles below: rows that do not exist (edge tiles,
   // the tail of the last CTA) get all-zero weights, so they scatter nothing and never write.
   RowWalk<DL, THREADS, ORDER> walk;
@@ -865,8 +869,10 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
       const int pt = sub + i * LANES;
       const bool on = cur.live && pt < NP;
       early_xy[i] = on ? __ldg(reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2) + pt) : make_float2(0.f, 0.f);
-      early_w[i] = on ? __ldg(w + cur.row * (int64_t)NP + pt) : 0.0f;
+      early_w[i] = (on && !FUSED) ? __ldg(w + cur.row * (int64_t)NP + pt) : 0.0f;
     }
+    if constexpr (FUSED)
+      early_sum = row_softmax<LANES, 4>(w + cur.row * (int64_t)NP, reinterpret_cast<float*>(s_fin) + 3, NP, sub);
     load_levels_plain(tab, shapes, lsi, L);
   } else {
     if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
@@ -902,8 +908,8 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     {
       const float2* lp = reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2);
       const float* wp = w + cur.row * (int64_t)NP;
-      float sm_sum = 1.0f;
-      if constexpr (FUSED) sm_sum = row_softmax<LANES, 4>(wp, reinterpret_cast<float*>(s_fin) + 3, NP, sub);
+      float sm_sum = early_sum;
+      if constexpr (FUSED && !EARLY) sm_sum = row_softmax<LANES, 4>(wp, reinterpret_cast<float*>(s_fin) + 3, NP, sub);
       // one record from a point's raw location / weight (FUSED: raw offset; the weight comes from the softmax);
       // rows that do not exist get all-zero records
       auto build = [&](int pt, float2 xy, float aw) {

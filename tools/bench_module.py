@@ -35,7 +35,7 @@ class RefKernelFunction(torch.autograd.Function):
         return gv, None, None, gl, gw, None
 
 
-def run(kind, batch, iters, mode, dev="cuda:0", amp=None):
+def run(kind, batch, iters, mode, dev="cuda:0", amp=None, masked=False):
     levels = LEVELS["dino_r50"]
     shapes, lsi = level_tensors(levels, dev)
     S = sum(h * w for h, w in levels)
@@ -57,6 +57,16 @@ def run(kind, batch, iters, mode, dev="cuda:0", amp=None):
             ref = torch.rand(batch, Q, 4, 2 if kind == "encoder" else 4, device=dev)
             go = torch.randn(batch, Q, 256, device=dev)
             sets.append((q, val, ref, go))
+        # batch-padding pattern: the right ~10 % of every level of every second image is padding
+        mask = None
+        if masked:
+            mask = torch.zeros(batch, S, dtype=torch.bool, device=dev)
+            start = 0
+            for h, w in levels:
+                mm = torch.zeros(h, w, dtype=torch.bool, device=dev)
+                mm[:, (9 * w) // 10:] = True
+                mask[1::2, start:start + h * w] = mm.reshape(-1)
+                start += h * w
         times = []
         for it in range(iters + 3):
             q, val, ref, go = sets[it % 3]
@@ -65,7 +75,8 @@ def run(kind, batch, iters, mode, dev="cuda:0", amp=None):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             with torch.autocast("cuda", dtype=amp, enabled=amp is not None):
-                out = m(q, value=val, reference_points=ref, spatial_shapes=shapes, level_start_index=lsi)
+                out = m(q, value=val, key_padding_mask=mask, reference_points=ref, spatial_shapes=shapes,
+                        level_start_index=lsi)
             out.backward(go.to(out.dtype))
             e1.record()
             torch.cuda.synchronize()
@@ -75,7 +86,7 @@ def run(kind, batch, iters, mode, dev="cuda:0", amp=None):
         msda_module.MultiScaleDeformableAttnFunction = saved
     pts = batch * Q * 8 * 4 * 4
     t = statistics.median(times)
-    return {"kind": kind, "batch": batch, "mode": mode, "amp": str(amp), "ms": round(t, 3),
+    return {"kind": kind, "batch": batch, "mode": mode, "amp": str(amp), "key_padding_mask": masked, "ms": round(t, 3),
             "gpts_s": round(pts / t / 1e6, 3)}
 
 
@@ -128,8 +139,17 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--out", default="")
+    ap.add_argument("--mask-only", action="store_true", help="only the key_padding_mask comparison (fused vs unfused)")
     a = ap.parse_args()
     rows = []
+    for kind in ("encoder", "decoder"):
+        for mode in ("fused", "unfused"):
+            for amp in (None, torch.bfloat16):
+                r = run(kind, a.batch, a.iters, mode, amp=amp, masked=True)
+                rows.append(r)
+                print(json.dumps(r), flush=True)
+    if a.mask_only:
+        return
     for kind in ("encoder", "decoder"):
         for b in sorted({a.batch, 1}):
             for mode in ("fused", "unfused", "reference_kernels"):
