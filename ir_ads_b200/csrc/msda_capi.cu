@@ -190,13 +190,7 @@ constexpr int bwd_threads(int threads, int order) { return (order == 0 || order 
 
 // channels per lane: 8 for bf16 rows of 32+ channels (16-byte lane loads), else 4
 template <int D, typename VT>
-constexpr int cpl_of() {
-#ifdef MSDA_EXP_F32_CPL8   // experiment builds: float rows with 256-bit lane loads (4 lanes per 128-byte row)
-  return D >= 32 ? 8 : 4;
-#else
-  return (sizeof(VT) == 2 && D >= 32) ? 8 : 4;
-#endif
-}
+constexpr int cpl_of() { return (sizeof(VT) == 2 && D >= 32) ? 8 : 4; }
 
 template <int D, typename VT, int PT, int THREADS, int TILED, int PRE = 0>
 int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,

@@ -82,17 +82,10 @@ __device__ __forceinline__ Vec<N> vzero() {
 }
 template <int N>
 __device__ __forceinline__ Vec<N> ldv(const float* p) {
-  Vec<N> r;
-  if constexpr (N == 4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-  } else {   // 256-bit lane load (sm_100: SASS LDG.E.ENL2.256); experiment builds only, see cpl_of in msda_capi.cu
-    static_assert(N == 8, "float rows use 4 or 8 channels per lane");
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
-                   "=f"(r.v[7])
-                 : "l"(p));
-  }
+  static_assert(N == 4, "float rows use 4 channels per lane");
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  Vec<4> r;
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
   return r;
 }
 template <int N>
@@ -113,8 +106,8 @@ __device__ __forceinline__ Vec<N> ldv(const __nv_bfloat16* p) {
 }
 template <int N>
 __device__ __forceinline__ void stv(float* p, const Vec<N>& a) {
-#pragma unroll
-  for (int i = 0; i < N; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(a.v[i], a.v[i + 1], a.v[i + 2], a.v[i + 3]);
+  static_assert(N == 4, "float rows use 4 channels per lane");
+  *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
 }
 __device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
