@@ -342,6 +342,28 @@ def test_deterministic_backward_scale_extremes():
     assert not zero.any()
 
 
+def test_deterministic_cell_reduce_edge_inputs():
+    """Dense deterministic path (one-pass cell reduce) on inputs built to stress its bookkeeping: almost every
+    point of an image out of range (entry slices that start in the middle of a cell and runs of empty cells),
+    every point in ONE cell (a cell spanning many 64-entry slices), and nothing in range at all."""
+    _, _lib, _, workloads, msda_c, _ = _mods()
+    levels = [(9, 13), (5, 7), (3, 4)]
+    value, shapes, lsi, loc, w = workloads.make_inputs(levels, 3, 700, 4, 32, 4, "decoder", "test", 29)
+    loc = loc.clone()
+    loc[0, 5:] = 7.5                                  # image 0: only 5 queries sample anything
+    loc[1] = torch.tensor([0.31, 0.62])               # image 1: every point of every level in one cell per level
+    go = torch.randn(3, 700, 128, generator=torch.Generator().manual_seed(3))
+    a = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_DETERMINISTIC)
+    b = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_DETERMINISTIC | _lib.FLAG_DET_ATOMIC)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    rgv, _, _ = msda_c.backward(go.numpy(), value.numpy(), shapes.numpy(), lsi.numpy(), loc.numpy(), w.numpy(), np.float64)
+    assert_close(a[1], rgv, 1e-5, 1e-6, "cell-reduce grad_value vs oracle")
+    loc[:] = -3.0                                     # nothing in range: no entries at all
+    z = run_cuda(value, shapes, lsi, loc, w, go, flags=_lib.FLAG_DETERMINISTIC)
+    assert not z[0].any() and not z[1].any() and not z[2].any() and not z[3].any()
+
+
 # ------------------------------------------------------------------------------------------------
 # bookkeeping: bit-exact
 # ------------------------------------------------------------------------------------------------
