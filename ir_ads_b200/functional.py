@@ -261,7 +261,12 @@ class MSDeformAttnFusedFunction(Function):
         grad_value = torch.empty_like(value)
         grad_off = torch.empty_like(sampling_offsets)
         grad_logits = torch.empty_like(attn_logits)
-        flags = _flags(True) & ~_lib.FLAG_DETERMINISTIC
+        flags = _flags(True)
+        # the fused kernels have no bit-reproducible backward: say so instead of quietly running the float reds
+        # (the module checks fused_supported(), which is False in deterministic mode, and composes the unfused op)
+        _require(not (flags & _lib.FLAG_DETERMINISTIC),
+                 "MSDeformAttnFusedFunction has no deterministic backward; use MultiScaleDeformableAttnFunction "
+                 "(module.fuse_pre_ops = False) under torch.use_deterministic_algorithms / set_deterministic")
         tag = _DTYPE_TAG[value.dtype]
         handle = _lib.lib()
         ws_bytes = int(handle.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, tag, flags))

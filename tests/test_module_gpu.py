@@ -221,6 +221,39 @@ def test_fused_function_folds_the_padding_mask(ref_dim, D, L, P, dtype):
     assert torch.equal(out_c, out_a)
 
 
+def test_fused_function_refuses_deterministic_mode():
+    """No silent downgrade: the fused kernels have no bit-reproducible backward, so asking for one raises; the
+    module falls back to the unfused composition (whose backward honours the flag) on its own."""
+    from ir_ads_b200 import MultiScaleDeformableAttention, functional
+    from ir_ads_b200.functional import MSDeformAttnFusedFunction
+    from ir_ads_b200.workloads import level_tensors
+
+    levels = [(6, 9), (3, 5)]
+    shapes, lsi = level_tensors(levels, DEV)
+    S = sum(h * w for h, w in levels)
+    value = torch.randn(1, S, 2, 32, device=DEV, requires_grad=True)
+    offsets = torch.randn(1, 7, 2, 2, 4, 2, device=DEV, requires_grad=True)
+    logits = torch.randn(1, 7, 2, 8, device=DEV, requires_grad=True)
+    ref = torch.rand(1, 7, 2, 2, device=DEV)
+    out = MSDeformAttnFusedFunction.apply(value, shapes, lsi, offsets, logits, ref)
+    functional.set_deterministic(True)
+    try:
+        with pytest.raises(RuntimeError, match="deterministic"):
+            out.sum().backward()
+        m = MultiScaleDeformableAttention(embed_dim=64, num_heads=2, num_levels=2, num_points=4, dropout=0.0,
+                                          batch_first=True).to(DEV)
+        q = torch.randn(1, S, 64, device=DEV, requires_grad=True)
+        runs = []
+        for _ in range(2):
+            q.grad = None
+            m(q, reference_points=torch.rand(1, S, 2, 2, device=DEV, generator=torch.Generator(DEV).manual_seed(1)),
+              spatial_shapes=shapes, level_start_index=lsi).square().sum().backward()
+            runs.append(q.grad.clone())
+        assert torch.equal(runs[0], runs[1])
+    finally:
+        functional.set_deterministic(False)
+
+
 @pytest.mark.parametrize("ref_dim", [2, 4])
 def test_module_fused_and_unfused_paths_agree(ref_dim):
     from ir_ads_b200 import MultiScaleDeformableAttention
