@@ -398,7 +398,7 @@ def run_e2e(wl, layers, dev, dist_on, world, args):
     h2d = sum(t.numel() * t.element_size() for t in host_in)
     d2h = sum(t.numel() * t.element_size() for t in host_out)
     L = len(layers)
-    steps = max(2, min(args.steps, 5))
+    steps = max(2, min(args.steps, 10))   # the pipeline fills and drains once per measurement: amortise it
     s_in, s_cmp, s_out = (torch.cuda.Stream(dev) for _ in range(3))
     dev_in = [[torch.empty_like(t, device=dev) for t in host_in] for _ in range(2)]
     ev = lambda: torch.cuda.Event()
