@@ -26,6 +26,13 @@ struct DetScale {
   float inv_scale;  // 2^-k (NaN when the inputs were not finite)
 };
 
+// One fixed-point contribution is round((w * scale) * g): the corner weight w (bilinear weight x attention weight)
+// is scaled first -- scale is a power of two, so that product is exact -- which leaves ONE multiplication per
+// channel.  The three deterministic paths of the fast shapes (fixed-point reds in msda_fast.cuh, per-pixel gather and
+// cell reduce in msda_det.cuh) form their contributions with exactly this expression, which is what makes their
+// results bit-identical.  (The product only differs from (w * g) * scale when w * g is subnormal.)
+__device__ __forceinline__ float det_weight(float w, float scale) { return __fmul_rn(w, scale); }
+
 template <typename T>
 struct AxisSplit {
   int low;     // floor(coord) (0 when !ok)

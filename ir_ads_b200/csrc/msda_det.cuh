@@ -74,10 +74,14 @@ det_bin_kernel(const float* __restrict__ loc, const float* __restrict__ w, const
   const int NP = L * P;
   for (int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pt < n_points;
        pt += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = pt / NP;
-    const int l = (int)(pt - row * NP) / P;
-    const int h = (int)(row % H);
-    const int64_t b = row / H / Q;
+    // 32-bit index arithmetic: the sorted path is only taken when n_points < 2^31 (det_sorted_ok), and this kernel
+    // was bound by its 64-bit divisions (issue slots 79 % busy at cfg 5)
+    const unsigned p32 = (unsigned)pt;
+    const unsigned row = p32 / (unsigned)NP;
+    const int l = (int)((p32 - row * (unsigned)NP) / (unsigned)P);
+    const unsigned bq = row / (unsigned)H;
+    const int h = (int)(row - bq * (unsigned)H);
+    const int64_t b = bq / (unsigned)Q;
     const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pt);
     const Cell<float> c = locate<float>(xy.x, xy.y, tab.H[l], tab.W[l]);
     if (c.valid == 0u) continue;
@@ -202,12 +206,12 @@ det_gather_kernel(const VT* __restrict__ grad_out, const int4* __restrict__ entr
         const int4 ent = __ldg(entries + e);
         const float lw = __int_as_float(ent.y), lh = __int_as_float(ent.z), aw = __int_as_float(ent.w);
         const float hh = 1.0f - lh, hw = 1.0f - lw;
-        const float c = (k == 0 ? hh * hw : (k == 1 ? hh * lw : (k == 2 ? lh * hw : lh * lw))) * aw;
+        const float c = det_weight((k == 0 ? hh * hw : (k == 1 ? hh * lw : (k == 2 ? lh * hw : lh * lw))) * aw, scale);
         const float4 go = ld4(grad_out + (int64_t)ent.x * D + sub * 4);
-        a0 += __float2ll_rn((c * go.x) * scale);
-        a1 += __float2ll_rn((c * go.y) * scale);
-        a2 += __float2ll_rn((c * go.z) * scale);
-        a3 += __float2ll_rn((c * go.w) * scale);
+        a0 += __float2ll_rn(c * go.x);
+        a1 += __float2ll_rn(c * go.y);
+        a2 += __float2ll_rn(c * go.z);
+        a3 += __float2ll_rn(c * go.w);
       }
     }
   }
@@ -321,11 +325,12 @@ det_cell_reduce_kernel(const VT* __restrict__ grad_out, const int4* __restrict__
     }
     const float lw = __int_as_float(ent.y), lh = __int_as_float(ent.z), aw = __int_as_float(ent.w);
     const float hh = 1.0f - lh, hw = 1.0f - lw;
-    const float c[4] = {hh * hw * aw, hh * lw * aw, lh * hw * aw, lh * lw * aw};
+    const float c[4] = {det_weight(hh * hw * aw, scale), det_weight(hh * lw * aw, scale),
+                        det_weight(lh * hw * aw, scale), det_weight(lh * lw * aw, scale)};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[k][i] += __float2ll_rn((c[k] * g[i]) * scale);
+      for (int i = 0; i < 4; ++i) a[k][i] += __float2ll_rn(c[k] * g[i]);
     ent = ent1;
     ent1 = ent2;
 #pragma unroll
