@@ -311,10 +311,11 @@ struct RowWalk {
         b = (int)(bh / H);
         h = (int)(bh - (int64_t)b * H);
       } else {
-        h = (int)(item % H);
-        const int64_t bc = item / H;
-        q = (int)(bc % chunks) * G::RPC + rin;
-        b = (int)(bc / chunks);
+        // item = blockIdx.x fits 32 bits: unsigned arithmetic instead of three 64-bit divisions per thread
+        const unsigned it = (unsigned)item, bc = it / (unsigned)H, bb = bc / (unsigned)chunks;
+        h = (int)(it - bc * (unsigned)H);
+        q = (int)(bc - bb * (unsigned)chunks) * G::RPC + rin;
+        b = (int)bb;
       }
       r.live = q < Q;
       r.b = b;
