@@ -221,6 +221,56 @@ def test_fused_function_folds_the_padding_mask(ref_dim, D, L, P, dtype):
     assert torch.equal(out_c, out_a)
 
 
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_fused_function_random_shapes_against_composition(seed):
+    """Seeded fuzz of the fused path (softmax + location affine + optional padding mask inside the kernels) against
+    the step-by-step composition around the plain op, over levels / B / Q / H / D / P / ref_dim / dtype."""
+    import numpy as np
+    from ir_ads_b200.functional import MSDeformAttnFusedFunction, fused_supported
+    from ir_ads_b200.workloads import level_tensors
+
+    rng = np.random.default_rng(500 + seed)
+    L = int(rng.integers(1, 5))
+    levels, h, w = [], int(rng.integers(3, 30)), int(rng.integers(3, 30))
+    for _ in range(L):
+        levels.append((h, w))
+        h, w = max(1, (h + 1) // 2), max(1, (w + 1) // 2)
+    B, H = int(rng.integers(1, 4)), int(rng.choice([1, 2, 4, 8]))
+    D = int(rng.choice([16, 32, 64, 128]))
+    P = int(rng.integers(1, 9))
+    Q = int(rng.integers(1, 150))
+    ref_dim = int(rng.choice([2, 4]))
+    dtype = torch.bfloat16 if rng.integers(0, 3) == 0 else torch.float32
+    masked = bool(rng.integers(0, 2))
+    torch.manual_seed(seed)
+    shapes, lsi = level_tensors(levels, DEV)
+    S = sum(a * b for a, b in levels)
+    value = torch.randn(B, S, H, D, device=DEV).to(dtype)
+    assert fused_supported(value, L, P)
+    offsets = torch.randn(B, Q, H, L, P, 2, device=DEV) * 3.0
+    logits = torch.randn(B, Q, H, L * P, device=DEV) * 2.0
+    ref = torch.rand(B, Q, L, ref_dim, device=DEV) * 1.3 - 0.15
+    if ref_dim == 4:
+        ref[..., 2:] = ref[..., 2:].abs() * 0.4 + 0.05
+    mask = (torch.rand(B, S, device=DEV) < 0.35) if masked else None
+    go = torch.randn(B, Q, H * D, device=DEV).to(dtype)
+
+    la = [t.clone().requires_grad_(True) for t in (value, offsets, logits)]
+    MSDeformAttnFusedFunction.apply(la[0], shapes, lsi, la[1], la[2], ref, mask).backward(go)
+    out_a = MSDeformAttnFusedFunction.apply(value, shapes, lsi, offsets, logits, ref, mask)
+    lb = [t.clone().requires_grad_(True) for t in (value, offsets, logits)]
+    vb = lb[0] if mask is None else lb[0].masked_fill(mask[..., None, None], 0.0)
+    out_b = _compose_unfused(vb, shapes, lsi, lb[1], lb[2], ref, P)
+    out_b.backward(go)
+    what = f"levels={levels} B={B} Q={Q} H={H} D={D} P={P} ref_dim={ref_dim} {dtype} masked={masked}"
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    gtol = 1e-4 if dtype == torch.float32 else 1e-2
+    for a, b, t, name in ((out_a, out_b, tol, "out"), (la[0].grad, lb[0].grad, tol, "grad_value"),
+                          (la[1].grad, lb[1].grad, gtol, "grad_offsets"), (la[2].grad, lb[2].grad, gtol, "grad_logits")):
+        a, b = a.double(), b.double()
+        assert (a - b).abs().max() <= t * b.abs().max() + 1e-6, (name, what, float((a - b).abs().max()), float(b.abs().max()))
+
+
 def test_fused_function_refuses_deterministic_mode():
     """No silent downgrade: the fused kernels have no bit-reproducible backward, so asking for one raises; the
     module falls back to the unfused composition (whose backward honours the flag) on its own."""

@@ -478,10 +478,11 @@ def test_full_size_properties(cfg):
         assert_close(got, ref, rt, 1e-6, f"{cfg} rows b={b}")
 
 
-@pytest.mark.parametrize("seed", list(range(16)))
+@pytest.mark.parametrize("seed", list(range(24)))
 def test_random_problem_shapes_against_oracle(seed):
     """Seeded fuzz over (levels, B, Q, H, D, P, dtype, distribution, flags): forward and all three gradients against the
-    fp64 C oracle, through whichever kernels the shape dispatches to (fast, generic, every row order, coarse split)."""
+    fp64 C oracle, through whichever kernels the shape dispatches to (fast, generic, every row order, coarse split,
+    the deterministic paths: fixed-point reds, per-pixel gather, cell reduce)."""
     _, _lib, _, workloads, msda_c, _ = _mods()
     rng = np.random.default_rng(1000 + seed)
     L = int(rng.integers(1, 6))
@@ -497,7 +498,9 @@ def test_random_problem_shapes_against_oracle(seed):
     dist = str(rng.choice(["model", "test", "edge"]))
     dtype = torch.bfloat16 if (rng.integers(0, 4) == 0) else torch.float32
     flag_choices = [0, _lib.FLAG_ORDER_LINEAR, _lib.FLAG_ORDER_STRIP, _lib.FLAG_ORDER_STRIP | _lib.FLAG_STRIP_HEAD_MAJOR,
-                    _lib.FLAG_COARSE_ON, _lib.FLAG_COARSE_ON | _lib.FLAG_COARSE_SERIAL, _lib.FLAG_FORCE_GENERIC]
+                    _lib.FLAG_COARSE_ON, _lib.FLAG_COARSE_ON | _lib.FLAG_COARSE_SERIAL, _lib.FLAG_FORCE_GENERIC,
+                    _lib.FLAG_DETERMINISTIC, _lib.FLAG_DETERMINISTIC | _lib.FLAG_DET_ATOMIC,
+                    _lib.FLAG_DETERMINISTIC | _lib.FLAG_FORCE_GENERIC]
     if encoder:
         flag_choices += [_lib.FLAG_ORDER_TILED, _lib.FLAG_ORDER_TILE2D]
     flags = int(rng.choice(flag_choices))
