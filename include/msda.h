@@ -103,6 +103,13 @@ extern "C" {
 #define MSDA_FLAG_COARSE_ON (1u << 8)     /* use it                                                        */
 #define MSDA_FLAG_COARSE_SERIAL (1u << 9) /* both kernels on `stream`, one after the other                */
 
+/* Backward: the caller does not need grad_value (autograd: value.requires_grad is False, e.g. a frozen memory
+ * branch).  On the shapes the fast kernels cover (msda_dispatch_name(..., backward=1) is "bwd_fast_...") the
+ * grad_value scatter -- the dominant cost of the backward -- is compiled out: grad_value may be NULL and is left
+ * untouched, no workspace is needed, grad_sampling_loc / grad_attn_weight are as always.  Elsewhere the flag is
+ * ignored and grad_value must be a valid buffer. */
+#define MSDA_FLAG_NO_GRAD_VALUE (1u << 11)
+
 int msda_abi_version(void);
 
 /* Forward.  Returns MSDA_OK or an error code.  B*Q*H*D == 0 is a no-op. */

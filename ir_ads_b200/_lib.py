@@ -29,6 +29,7 @@ FLAG_COARSE_OFF = 1 << 7
 FLAG_COARSE_ON = 1 << 8
 FLAG_COARSE_SERIAL = 1 << 9
 FLAG_STRIP_HEAD_MAJOR = 1 << 10
+FLAG_NO_GRAD_VALUE = 1 << 11
 ABI_VERSION = 2
 
 _lock = threading.Lock()

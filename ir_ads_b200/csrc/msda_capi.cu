@@ -756,6 +756,16 @@ int msda_backward_hs(void* stream, const void* grad_output, const void* value, c
   const size_t es = elem_size(dtype);
   const size_t ls = dtype == MSDA_F64 ? 8 : 4;
   if (d.n_value() == 0 && d.n_points() == 0) return MSDA_OK;
+  if ((flags & MSDA_FLAG_NO_GRAD_VALUE) && d.n_value() != 0 && d.n_points() != 0 && fast_ok(d, dtype, flags)) {
+    // grad_value not wanted: the regular kernel with the scatter compiled out (no zero-fill, no workspace)
+    if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight ||
+        !grad_sampling_loc || !grad_attn_weight)
+      return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    DeviceGuard guard_ns;
+    MSDA_CUDA(guard_ns.enter(value));
+    return bwd_fast_noscatter(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                              attn_weight, grad_sampling_loc, grad_attn_weight);
+  }
   const void* anchor = d.n_value() ? grad_value : grad_attn_weight;
   if (!anchor) return fail(MSDA_ERR_INVALID_ARGUMENT, "gradient output pointer is null");
   DeviceGuard guard;

@@ -127,17 +127,35 @@ def ms_deform_attn_backward(value: torch.Tensor, spatial_shapes: torch.Tensor, l
                             sampling_loc: torch.Tensor, attn_weight: torch.Tensor, grad_output: torch.Tensor,
                             im2col_step: int = 64) -> List[torch.Tensor]:
     """``detrex._C.ms_deform_attn_backward`` (vision.cpp:56): ``[grad_value, grad_sampling_loc, grad_attn_weight]``."""
+    return _backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, True)
+
+
+def _backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+              need_grad_value: bool) -> List[torch.Tensor]:
+    """The backward behind ms_deform_attn_backward.  ``need_grad_value=False`` (the autograd Function passes it when
+    ``value`` does not require grad, e.g. a frozen memory branch) returns ``None`` for ``grad_value`` and, on the
+    shapes the fast kernels cover, skips its scatter -- the dominant cost of the backward -- altogether."""
     B, S, H, D, L, Q, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
     _require(grad_output.is_cuda and grad_output.device == value.device, "grad_output must be a CUDA tensor")
     _require(grad_output.dtype == value.dtype, "grad_output dtype must match value")
     _require(grad_output.numel() == B * Q * H * D, "grad_output must be [B, Q, H*D]")
     grad_output = grad_output.contiguous()
-    grad_value = torch.empty_like(value)
     grad_loc = torch.empty_like(sampling_loc)
     grad_w = torch.empty_like(attn_weight)
     flags = _flags(True)
     tag = _DTYPE_TAG[value.dtype]
     handle = _lib.lib()
+    skip_scatter = (not need_grad_value and B * S * D > 0 and Q * L * P > 0
+                    and b"_fast_" in handle.msda_dispatch_name(D, L, P, S, H, tag, flags, 1))
+    if skip_scatter:
+        status = handle.msda_backward_hs(
+            ctypes.c_void_p(torch.cuda.current_stream(value.device).cuda_stream), _ptr(grad_output), _ptr(value),
+            _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc), _ptr(attn_weight), B, S, H, D, L, Q, P,
+            ctypes.c_void_p(0), _ptr(grad_loc), _ptr(grad_w), ctypes.c_void_p(0), 0, tag,
+            flags | _lib.FLAG_NO_GRAD_VALUE, ctypes.c_void_p(0))
+        _lib.check(status, "ms_deform_attn_backward")
+        return [None, grad_loc, grad_w]
+    grad_value = torch.empty_like(value)
     ws_bytes = int(handle.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, tag, flags))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
     stream = torch.cuda.current_stream(value.device).cuda_stream
@@ -149,7 +167,7 @@ def ms_deform_attn_backward(value: torch.Tensor, spatial_shapes: torch.Tensor, l
                                      ctypes.cast(host_shapes, ctypes.c_void_p) if host_shapes is not None
                                      else ctypes.c_void_p(0))
     _lib.check(status, "ms_deform_attn_backward")
-    return [grad_value, grad_loc, grad_w]
+    return [grad_value if need_grad_value else None, grad_loc, grad_w]
 
 
 class MultiScaleDeformableAttnFunction(Function):
@@ -169,9 +187,9 @@ class MultiScaleDeformableAttnFunction(Function):
     @once_differentiable
     def backward(ctx, grad_output):
         value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = ctx.saved_tensors
-        grad_value, grad_sampling_loc, grad_attn_weight = ms_deform_attn_backward(
+        grad_value, grad_sampling_loc, grad_attn_weight = _backward(
             value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights, grad_output,
-            ctx.im2col_step)
+            need_grad_value=ctx.needs_input_grad[0])
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
 
 

@@ -364,6 +364,29 @@ def test_deterministic_cell_reduce_edge_inputs():
     assert not z[0].any() and not z[1].any() and not z[2].any() and not z[3].any()
 
 
+def test_backward_skips_the_scatter_when_value_needs_no_grad():
+    """autograd tells the Function that `value` needs no gradient (frozen memory branch): the fast path then runs the
+    backward kernel with the grad_value scatter compiled out -- same grad_loc / grad_w bits, no grad for value -- and
+    the generic path simply drops the gradient."""
+    ir, _lib, functional, workloads, _, _ = _mods()
+    for D in (32, 30):                                   # fast kernels / generic kernels
+        value, shapes, lsi, loc, w = workloads.make_inputs([(9, 13), (5, 7)], 2, 60, 4, D, 4, "decoder", "model", 8)
+        go = torch.randn(2, 60, 4 * D, generator=torch.Generator().manual_seed(1)).to(DEV)
+        shapes, lsi = shapes.to(DEV), lsi.to(DEV)
+        res = {}
+        for need in (True, False):
+            v = value.to(DEV).requires_grad_(need)
+            lo, ww = loc.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+            out = ir.MultiScaleDeformableAttnFunction.apply(v, shapes, lsi, lo, ww, 64)
+            before = _lib.launch_count()
+            out.backward(go)
+            res[need] = (v.grad, lo.grad.clone(), ww.grad.clone(), _lib.launch_count() - before)
+        assert res[True][0] is not None and res[False][0] is None
+        assert torch.equal(res[True][1], res[False][1]) and torch.equal(res[True][2], res[False][2])
+        assert res[False][3] >= 1                        # the CUDA kernels ran in both cases
+
+
+
 # ------------------------------------------------------------------------------------------------
 # bookkeeping: bit-exact
 # ------------------------------------------------------------------------------------------------
