@@ -38,7 +38,7 @@
  *                                          (fully written by the library, no pre-zeroing needed)
  *
  * Thread safety: re-entrant, no global mutable state except a launch counter and a
- * thread-local last-error string.  Work is enqueued on `stream` of the device that owns `value`
+ * thread-local last-error string; no library-owned streams, events or locks.  Work is enqueued on `stream` of the device that owns `value`
  * (the library switches to that device for the call and restores the previous one).
  */
 #ifndef MSDA_B200_H_
@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 2
+#define MSDA_ABI_VERSION 3
 
 /* dtype tags */
 #define MSDA_F32 0  /* value/out/grads float,  loc/w float  */
@@ -79,29 +79,26 @@ extern "C" {
  * (msda_det.cuh) is available (A/B testing; both give the same bits). */
 #define MSDA_FLAG_DET_ATOMIC (1u << 6)
 #define MSDA_FLAG_FORCE_GENERIC (1u << 1) /* bypass the D in {16,32,64,128} fast kernels             */
-#define MSDA_FLAG_ORDER_LINEAR (1u << 2)  /* rows processed in memory order (the default)              */
-/* Encoder form only (Q == S): persistent CTAs walk (image, pyramid tile, head) work items so that a
- * tile's gather footprint stays in L1.  Same results; measured slower than LINEAR so far,
- * hence opt-in. */
-#define MSDA_FLAG_ORDER_TILED (1u << 3)
+/* Row order = which rows a CTA works on.  A scheduling choice only: results never depend on it.  Without an order
+ * flag the library picks (forward: LINEAR; backward: the folding encoder kernel when it applies, else STRIP). */
+#define MSDA_FLAG_ORDER_LINEAR (1u << 2)  /* rows in memory order (b, q, h)                              */
 /* One CTA = a strip of consecutive queries of ONE head (any Q): x-adjacent queries re-use corner lines in L1. */
 #define MSDA_FLAG_ORDER_STRIP (1u << 4)
-/* Encoder form only (Q == S): one CTA = an 8x4-pixel tile (at D=32) of one level and ONE head, non-persistent. */
+/* Encoder form only (Q == S): one CTA = a pixel tile (8x4 at D=32) of one level and ONE head. */
 #define MSDA_FLAG_ORDER_TILE2D (1u << 5)
-/* STRIP order: strips ordered (image, head, strip) instead of (image, strip, head), so that the CTAs resident on
- * an SM work on the same head (A/B testing; measured no faster). */
-#define MSDA_FLAG_STRIP_HEAD_MAJOR (1u << 10)
-/* Backward (float accumulation, D in {32,64,128}), OPT-IN experiment: grad_value of the coarsest pyramid levels
- * -- as many as fit in ~200 KB of shared memory, decided on the device from the level shapes -- is pre-aggregated
- * on chip by a second, persistent kernel (one warp per level and pixel-parity class, no atomics;
- * csrc/msda_coarse.cuh) instead of one vector red per sample, which halves the L2 reduction traffic at pyramid
- * shapes.  With a host copy of the shapes (msda_backward_hs) the kernel runs concurrently with the main
- * backward kernel on a library-owned side stream that forks from / joins `stream`; serially on `stream` while
- * it is being graph-captured or without the host copy.  Same results up to float summation order.
- * Measured slower than the default all-reds backward on B200, hence never the default. */
-#define MSDA_FLAG_COARSE_OFF (1u << 7)    /* never use it (wins over COARSE_ON)                            */
-#define MSDA_FLAG_COARSE_ON (1u << 8)     /* use it                                                        */
-#define MSDA_FLAG_COARSE_SERIAL (1u << 9) /* both kernels on `stream`, one after the other                */
+/* Bits 3 and 7-10 selected round-1 experiments (persistent TILED order, shared-memory accumulation of the coarse
+ * levels on a side stream, head-major strips) that were measured slower and removed; they are reserved and
+ * ignored. */
+
+/* Backward, encoder form (Q == S, query i is pixel i of the pyramid), D in {32, 64}, float accumulation:
+ * grad_value contributions of an 8x8 query tile of one head are pre-added ON THE SM (pixel-keyed lists in
+ * shared memory, csrc/msda_fold.cuh) and leave it as ONE vector red per distinct destination row instead of one
+ * per (point, corner): ~5x fewer reds on model-like inputs (profiles/r02a_fold_rate_cfg2.json).
+ * grad_sampling_loc / grad_attn_weight are bit-identical to the other kernels'; grad_value differs by float
+ * summation order only.  FOLD_OFF wins over FOLD_ON; an explicit ORDER_* flag, MSDA_FLAG_DETERMINISTIC and
+ * MSDA_FLAG_FORCE_GENERIC also select the non-folding kernels. */
+#define MSDA_FLAG_FOLD_ON (1u << 12)
+#define MSDA_FLAG_FOLD_OFF (1u << 13)
 
 /* Backward: the caller does not need grad_value (autograd: value.requires_grad is False, e.g. a frozen memory
  * branch).  On the shapes the fast kernels cover (msda_dispatch_name(..., backward=1) is "bwd_fast_...") the
@@ -130,19 +127,6 @@ int msda_backward(void* stream, const void* grad_output, const void* value,
                   int num_heads, int channels, int num_levels, int num_query, int num_point,
                   void* grad_value, void* grad_sampling_loc, void* grad_attn_weight,
                   void* workspace, size_t workspace_bytes, int dtype, unsigned flags);
-
-/* msda_backward with an optional HOST copy of spatial_shapes ([L, 2] int64, may be NULL = msda_backward).
- * The library never reads device memory on the host, so without the copy it cannot know the level sizes; with
- * it, the shared-memory tile of the coarse-level accumulation (MSDA_FLAG_COARSE_*, below) is sized exactly and
- * that kernel shares every SM with the main backward kernel.  The copy must equal the device tensor; it is
- * only used to size launches, never for arithmetic (both kernels re-derive everything from the device shapes). */
-int msda_backward_hs(void* stream, const void* grad_output, const void* value,
-                     const int64_t* spatial_shapes, const int64_t* level_start_index,
-                     const void* sampling_loc, const void* attn_weight, int batch, int spatial_size,
-                     int num_heads, int channels, int num_levels, int num_query, int num_point,
-                     void* grad_value, void* grad_sampling_loc, void* grad_attn_weight,
-                     void* workspace, size_t workspace_bytes, int dtype, unsigned flags,
-                     const int64_t* spatial_shapes_host);
 
 /*
  * Fused module path (an extension, the reference has no counterpart): the
@@ -217,6 +201,10 @@ int msda_dcnv3_backward(void* stream, const void* grad_output, const void* input
  *                  corners inside `value`, -1 for a zero-padded corner or a gated-out point;
  *   frac           [B*Q*H*L*P, 2] float  (lw, lh) fractional weights.
  * Same definition as msda_oracle_bookkeeping in oracle/msda_oracle.c; compared bit for bit.
+ * On the shapes the fast kernels cover (float dispatch name "*_fast_*") the numbers are decoded from the very
+ * record the fast kernels build per point (clamped low-corner offset + alias / validity flags), i.e. they are
+ * the addresses those kernels gather from and scatter to; elsewhere they come from the generic kernels'
+ * coordinate code.
  */
 int msda_debug_bookkeeping(void* stream, const float* sampling_loc, const int64_t* spatial_shapes,
                            const int64_t* level_start_index, int batch, int spatial_size,

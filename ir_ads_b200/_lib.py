@@ -21,16 +21,13 @@ MSDA_OK = 0
 FLAG_DETERMINISTIC = 1 << 0
 FLAG_FORCE_GENERIC = 1 << 1
 FLAG_ORDER_LINEAR = 1 << 2
-FLAG_ORDER_TILED = 1 << 3
 FLAG_ORDER_STRIP = 1 << 4
 FLAG_ORDER_TILE2D = 1 << 5
 FLAG_DET_ATOMIC = 1 << 6
-FLAG_COARSE_OFF = 1 << 7
-FLAG_COARSE_ON = 1 << 8
-FLAG_COARSE_SERIAL = 1 << 9
-FLAG_STRIP_HEAD_MAJOR = 1 << 10
 FLAG_NO_GRAD_VALUE = 1 << 11
-ABI_VERSION = 2
+FLAG_FOLD_ON = 1 << 12
+FLAG_FOLD_OFF = 1 << 13
+ABI_VERSION = 3
 
 _lock = threading.Lock()
 _lib = None
@@ -62,8 +59,6 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_backward_workspace_bytes.argtypes = [i, i, i, i, i, i, i, i, u]
     lib.msda_backward.restype = i
     lib.msda_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, vp, vp, sz, i, u]
-    lib.msda_backward_hs.restype = i
-    lib.msda_backward_hs.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp, vp, vp, sz, i, u, vp]
     lib.msda_fused_supported.restype = i
     lib.msda_fused_supported.argtypes = [i, i, i, i, i, i, u]
     lib.msda_fused_forward.restype = i

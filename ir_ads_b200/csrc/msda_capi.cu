@@ -5,39 +5,24 @@
 // (/root/reference/detrex/layers/csrc/MsDeformAttn/ms_deform_attn_cuda.cu:21-154) and of the
 // kernel selector ms_deformable_col2im_cuda (ms_deform_im2col_cuda.cuh:956-1327), minus ATen:
 // no allocation, no im2col_step chunk loop (one launch covers the batch), errors returned.
-#include "../../include/msda.h"
-
-#include <cuda_bf16.h>
-#include <cuda_runtime.h>
+#include "msda_host.h"
 
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 
-#include "msda_fast.cuh"
 #include "msda_generic.cuh"
 #include "msda_det.cuh"
 
-namespace msda {
-// msda_coarse_launch.cu (kernel: msda_coarse.cuh)
-constexpr int kCoarseBatch = 32;
-constexpr int coarse_stage_bytes(int D, int elem_size, int L, int P) {
-  return kCoarseBatch * (D * elem_size + (L < kCoarseMaxLevels ? L : kCoarseMaxLevels) * P * 12);
-}
-cudaError_t launch_bwd_coarse(cudaStream_t st, bool value_is_bf16, const void* go, const int64_t* shapes,
-                              const int64_t* lsi, const float* loc, const float* w, float* gv, int B, int S, int H,
-                              int D, int L, int Q, int P, int budget);
-}  // namespace msda
-
 namespace {
-
 std::atomic<uint64_t> g_launches{0};
 thread_local char g_err[512] = "";
+}  // namespace
 
-int fail(int status, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+namespace msda_host {
+
 int fail(int status, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -51,11 +36,23 @@ int cuda_fail(cudaError_t e, const char* what) {
   return fail(MSDA_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
-#define MSDA_CUDA(call)                                   \
-  do {                                                    \
-    cudaError_t e__ = (call);                             \
-    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
-  } while (0)
+void count_launch() { count_launch(); }
+
+bool fast_ok(const Dims& d, int dtype, unsigned flags) {
+  if (flags & MSDA_FLAG_FORCE_GENERIC) return false;
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
+  if (!(d.D == 16 || d.D == 32 || d.D == 64 || d.D == 128)) return false;
+  if (d.L < 1 || d.L > msda::kFastMaxLevels) return false;
+  if (d.L * d.P < 1 || d.L * d.P > msda::kFastMaxPoints) return false;
+  // element offsets inside one image are 32-bit in the fast kernels (one spare row/pixel of slack)
+  if (((int64_t)d.S + 65536) * d.H * d.D >= ((int64_t)1 << 31)) return false;
+  return true;
+}
+
+}  // namespace msda_host
+
+namespace {
+using namespace msda_host;
 
 // Runs the call on the device that owns `ptr`, restoring the caller's device afterwards
 // (the reference has no guard at all: ms_deform_attn_cuda.cu:66 just takes the current stream).
@@ -80,27 +77,6 @@ struct DeviceGuard {
   }
 };
 
-// Experiment knobs, compiled in only with -DMSDA_EXPERIMENTS (tools/ablate.sh builds such variants into
-// build/variants/, never the product library; results with MSDA_EXP_SKIP_COARSE_KERNEL are WRONG on purpose):
-//   MSDA_EXP_BWD_SMEM_PAD=<bytes>   extra dynamic shared memory per CTA of the main backward kernel (occupancy study)
-//   MSDA_EXP_BWD_CARVEOUT=<percent> preferred shared-memory carveout of the main backward kernel (L1 size study)
-//   MSDA_EXP_SKIP_COARSE_KERNEL=1   plan the coarse-level split but do not launch the coarse kernel (times the rest)
-#ifdef MSDA_EXPERIMENTS
-int exp_env(const char* name) {
-  const char* v = std::getenv(name);
-  return v ? std::atoi(v) : 0;
-}
-#else
-constexpr int exp_env(const char*) { return 0; }
-#endif
-
-struct Dims {
-  int B, S, H, D, L, Q, P;
-  int64_t rows() const { return (int64_t)B * Q * H; }
-  int64_t n_value() const { return (int64_t)B * S * H * D; }
-  int64_t n_points() const { return rows() * L * P; }
-};
-
 int check_dims(const Dims& d, int dtype) {
   if (d.B < 0 || d.S < 0 || d.H < 0 || d.D < 0 || d.L < 0 || d.Q < 0 || d.P < 0)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "negative dimension (B=%d S=%d H=%d D=%d L=%d Q=%d P=%d)", d.B, d.S, d.H,
@@ -110,356 +86,36 @@ int check_dims(const Dims& d, int dtype) {
   return MSDA_OK;
 }
 
-bool fast_ok(const Dims& d, int dtype, unsigned flags) {
-  if (flags & MSDA_FLAG_FORCE_GENERIC) return false;
-  if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
-  if (!(d.D == 16 || d.D == 32 || d.D == 64 || d.D == 128)) return false;
-  if (d.L < 1 || d.L > msda::kFastMaxLevels) return false;
-  if (d.L * d.P < 1 || d.L * d.P > msda::kFastMaxPoints) return false;
-  // element offsets inside one image are 32-bit in the fast kernels (one spare row/pixel of slack)
-  if (((int64_t)d.S + 65536) * d.H * d.D >= ((int64_t)1 << 31)) return false;
-  return true;
-}
-
-int grid_for(int64_t work_items, int threads, int cap_blocks) {
-  int64_t g = (work_items + threads - 1) / threads;
-  if (g > cap_blocks) g = cap_blocks;
-  if (g < 1) g = 1;
-  return (int)g;
-}
-
-// ------------------------------------------------------------------------------------------
-// fast-kernel launch helpers
-// ------------------------------------------------------------------------------------------
-template <typename K>
-cudaError_t ensure_smem(K kernel, size_t bytes) {
-  if (bytes <= 48 * 1024) return cudaSuccess;
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-
-// Persistent (TILED) kernels run one wave: SM count x resident CTAs per SM.
-template <typename K>
-cudaError_t persistent_grid(K kernel, int threads, size_t smem, unsigned* grid) {
-  int dev = 0, sms = 0, per_sm = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-  *grid = (unsigned)(sms * per_sm);
-  return cudaSuccess;
-}
-
-// Row order: TILED needs query i == pixel i of the pyramid (encoder self-attention, Q == S).
-bool use_tiled(const Dims& d, unsigned flags) {
-  if (!(d.Q == d.S && (flags & MSDA_FLAG_ORDER_TILED) && !(flags & MSDA_FLAG_ORDER_LINEAR))) return false;
-  // the persistent 1024-thread CTAs stage records + raw loc/w for 4096/D rows; the row order is only a
-  // scheduling choice, so fall back to the default order when that does not fit in shared memory
-  const int NP = d.L * d.P, rpc = 1024 / (d.D / 8 > 0 ? d.D / 8 : 1);   // worst case: 8 channels per lane
-  const size_t words = (size_t)rpc * (size_t)(msda::bwd_row_words(NP, true) > msda::fwd_row_words(NP, true)
-                                                  ? msda::bwd_row_words(NP, true)
-                                                  : msda::fwd_row_words(NP, true));
-  return sizeof(msda::LevelTab) + words * 4 <= 200 * 1024;
-}
-bool use_strip(const Dims& d, unsigned flags) {
-  (void)d;
-  return (flags & MSDA_FLAG_ORDER_STRIP) && !(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED | MSDA_FLAG_ORDER_TILE2D));
-}
-bool use_tile2d(const Dims& d, unsigned flags) {
-  return d.Q == d.S && (flags & MSDA_FLAG_ORDER_TILE2D) && !(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED));
-}
-// TILE2D launches an upper bound on the tile count that needs only S and L (the level shapes stay on the
-// device): sum_l ceil(H_l/TH)*ceil(W_l/TW) is ~1.03 * S/RPC for image pyramids; 25 % + 32 tiles per level of
-// slack covers them, the kernel's grid-stride step covers anything else.
-int64_t tile2d_bound(const Dims& d, int rpc) { return ((int64_t)d.S + rpc - 1) / rpc * 5 / 4 + 32 * (int64_t)d.L; }
-
-// CTA sizes of the single-pass row orders (LINEAR, STRIP).  An SM re-uses a CTA's slot only when the CTA's slowest
-// warp is done, so small CTAs keep more warps busy: cfg 2 forward 0.665 / 0.635 / 0.620 ms at 256 / 128 / 64
-// threads, backward 1.687 / 1.672 / 1.695 ms (profiles/r01s_experiments.txt).  The tile orders keep their own.
-#ifndef MSDA_FWD_THREADS
-#define MSDA_FWD_THREADS 64
-#endif
-#ifndef MSDA_BWD_THREADS
-#define MSDA_BWD_THREADS 128
-#endif
-constexpr int kFwdThreads = MSDA_FWD_THREADS, kBwdThreads = MSDA_BWD_THREADS;
-constexpr int fwd_threads(int threads, int order) { return (order == 0 || order == 2) ? kFwdThreads : threads; }
-constexpr int bwd_threads(int threads, int order) { return (order == 0 || order == 2) ? kBwdThreads : threads; }
-
-// channels per lane: 8 for bf16 rows of 32+ channels (16-byte lane loads), else 4
-template <int D, typename VT>
-constexpr int cpl_of() { return (sizeof(VT) == 2 && D >= 32) ? 8 : 4; }
-
-template <int D, typename VT, int PT, int THREADS, int TILED, int PRE = 0>
-int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int64_t* shapes, const int64_t* lsi,
-                    const void* loc, const void* w, void* out, msda::FusedArgs fa = msda::FusedArgs{},
-                    int head_major = 0) {
-  constexpr int CPL = cpl_of<D, VT>();
-  using G = msda::Geom<D * 4 / CPL, THREADS>;
-  const int NP = d.L * d.P;
-  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::fwd_row_words(NP, TILED == 1) * 4;
-  auto k = msda::msda_fwd_fast_kernel<D, VT, PT, THREADS, TILED, PRE, CPL>;
-  MSDA_CUDA(ensure_smem(k, smem));
-  const int64_t rows = d.rows();
-  unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
-  if (TILED == 1) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
-  if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
-  if (TILED == 3) grid = (unsigned)((int64_t)d.B * d.H * tile2d_bound(d, G::RPC));
-  k<<<grid, THREADS, smem, st>>>((const VT*)value, shapes, lsi, (const float*)loc, (const float*)w, (VT*)out, fa,
-                                 d.B, d.S, d.H, d.L, d.Q, d.P, rows, head_major);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  MSDA_CUDA(cudaGetLastError());
-  return MSDA_OK;
-}
-
-template <int D, typename VT, int PT, int THREADS, int TILED, typename ACC, int PRE = 0>
-int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
-                    const int64_t* lsi, const void* loc, const void* w, ACC* gv, void* gl, void* gw,
-                    const msda::DetScale* det, msda::FusedArgs fa = msda::FusedArgs{}, int coarse_budget = 0,
-                    int head_major = 0) {
-  // The backward keeps 4 channels per lane for every type: it is bound by the grad_value reds, and those run
-  // fastest as one full 128-byte line per row and instruction (8 channels per lane -> two 64-byte halves per
-  // row: 1.75 -> 2.09 ms at cfg2 with bf16 value), so the faster 16-byte gather buys nothing there.
-  constexpr int CPL = 4;
-  using G = msda::Geom<D * 4 / CPL, THREADS>;
-  const int NP = d.L * d.P;
-  static const int exp_pad = exp_env("MSDA_EXP_BWD_SMEM_PAD");
-  const size_t smem = sizeof(msda::LevelTab) + (size_t)G::RPC * msda::bwd_row_words(NP, TILED == 1) * 4 + (size_t)exp_pad;
-  auto k = msda::msda_bwd_fast_kernel<D, VT, PT, THREADS, TILED, ACC, PRE, CPL>;
-  MSDA_CUDA(ensure_smem(k, smem));
-  static const int exp_carve = exp_env("MSDA_EXP_BWD_CARVEOUT");   // percent of the SM's 228 KB given to shared memory
-  if (exp_carve > 0) MSDA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, exp_carve));
-  const int64_t rows = d.rows();
-  unsigned grid = (unsigned)((rows + G::RPC - 1) / G::RPC);
-  if (TILED == 1) MSDA_CUDA(persistent_grid(k, THREADS, smem, &grid));
-  if (TILED == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
-  if (TILED == 3) grid = (unsigned)((int64_t)d.B * d.H * tile2d_bound(d, G::RPC));
-  k<<<grid, THREADS, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
-                                 gv, (float*)gl, (float*)gw, det, fa, d.B, d.S, d.H, d.L, d.Q, d.P, rows, coarse_budget,
-                                 head_major);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  MSDA_CUDA(cudaGetLastError());
-  return MSDA_OK;
-}
-
-#ifdef MSDA_EXP_SLIM
-// Kernel-variant experiment builds (tools/build_variant.sh): only D = 32, P in {4, 8}, LINEAR / STRIP orders are instantiated,
-// so a variant compiles in well under a minute.  Never defined for the product library.
-#define MSDA_DISPATCH_ORDER(D_, VT_, PT_, CALL)                                      \
-  do {                                                                               \
-    if (use_strip(d, flags)) return CALL(D_, VT_, PT_, 256, 2);                      \
-    return CALL(D_, VT_, PT_, 256, 0);                                               \
-  } while (0)
-#define MSDA_DISPATCH_PT(D_, VT_, CALL)                      \
-  do {                                                       \
-    if (d.P == 4) MSDA_DISPATCH_ORDER(D_, VT_, 4, CALL);     \
-    if (d.P == 8) MSDA_DISPATCH_ORDER(D_, VT_, 8, CALL);     \
-    return fail(MSDA_ERR_UNSUPPORTED, "slim build: P=%d", d.P); \
-  } while (0)
-#define MSDA_DISPATCH_D(VT_, CALL)                           \
-  do {                                                       \
-    switch (d.D) {                                           \
-      case 32: MSDA_DISPATCH_PT(32, VT_, CALL);              \
-      default: return fail(MSDA_ERR_UNSUPPORTED, "slim build: D=%d", d.D); \
-    }                                                        \
-  } while (0)
-#else
-#define MSDA_DISPATCH_ORDER(D_, VT_, PT_, CALL)                                      \
-  do {                                                                               \
-    if (use_tile2d(d, flags)) return CALL(D_, VT_, PT_, 256, 3);                     \
-    if (use_strip(d, flags)) return CALL(D_, VT_, PT_, 256, 2);                      \
-    if (!use_tiled(d, flags)) return CALL(D_, VT_, PT_, 256, 0);                     \
-    return CALL(D_, VT_, PT_, 1024, 1);                                              \
-  } while (0)
-
-#define MSDA_DISPATCH_PT(D_, VT_, CALL)                      \
-  do {                                                       \
-    if (d.P == 4) MSDA_DISPATCH_ORDER(D_, VT_, 4, CALL);     \
-    if (d.P == 8) MSDA_DISPATCH_ORDER(D_, VT_, 8, CALL);     \
-    MSDA_DISPATCH_ORDER(D_, VT_, 0, CALL);                   \
-  } while (0)
-
-#define MSDA_DISPATCH_D(VT_, CALL)                           \
-  do {                                                       \
-    switch (d.D) {                                           \
-      case 16: MSDA_DISPATCH_PT(16, VT_, CALL);              \
-      case 32: MSDA_DISPATCH_PT(32, VT_, CALL);              \
-      case 64: MSDA_DISPATCH_PT(64, VT_, CALL);              \
-      case 128: MSDA_DISPATCH_PT(128, VT_, CALL);            \
-      default: return fail(MSDA_ERR_UNSUPPORTED, "fast path: D=%d", d.D); \
-    }                                                        \
-  } while (0)
-#endif
-
-int fwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* value, const int64_t* shapes,
-             const int64_t* lsi, const void* loc, const void* w, void* out) {
-#define CALL_FWD(D_, VT_, PT_, TH_, TL_)                                                              \
-  launch_fwd_fast<D_, VT_, PT_, fwd_threads(TH_, TL_), TL_>(st, d, value, shapes, lsi, loc, w, out, msda::FusedArgs{}, \
-                                          (flags & MSDA_FLAG_STRIP_HEAD_MAJOR) ? 1 : 0)
-  if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_FWD);
-  MSDA_DISPATCH_D(__nv_bfloat16, CALL_FWD);
-#undef CALL_FWD
-}
-
-int bwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* go, const void* value,
-             const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl,
-             void* gw, int coarse_budget) {
-  // default row order of the backward: STRIP (measured 3 % faster than LINEAR at cfg 2: fewer L1 misses
-  // on the crossbar-bound kernel); the forward keeps LINEAR
-  if (!(flags & (MSDA_FLAG_ORDER_LINEAR | MSDA_FLAG_ORDER_TILED | MSDA_FLAG_ORDER_TILE2D))) flags |= MSDA_FLAG_ORDER_STRIP;
-#define CALL_BWD(D_, VT_, PT_, TH_, TL_) \
-  launch_bwd_fast<D_, VT_, PT_, bwd_threads(TH_, TL_), TL_, float>(st, d, go, value, shapes, lsi, loc, w, gv, gl, gw, nullptr, \
-                                                 msda::FusedArgs{}, coarse_budget,                                \
-                                                 (flags & MSDA_FLAG_STRIP_HEAD_MAJOR) ? 1 : 0)
-  if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
-  MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
-#undef CALL_BWD
-}
-
-// ---- shared-memory accumulation of the coarse levels (msda_coarse.cuh) ----
-constexpr int kCoarseBudget = 200 * 1024;   // most shared memory the resident grad_value tile may take
-
-// What the coarse-level accumulation gets for this problem.  budget == 0: not used.  Which levels are resident
-// is decided on the device from the level shapes and the budget; when the caller supplied a HOST copy of the
-// shapes the budget is exactly the resident levels' bytes (so the kernel leaves the rest of the SM's shared
-// memory to the main backward kernel and the two can share every SM), otherwise it is the upper bound and the
-// two kernels run one after the other.
-struct CoarsePlan {
-  int budget = 0;
-  bool exact = false;
-};
-CoarsePlan coarse_plan(const Dims& d, int dtype, unsigned flags, const int64_t* host_shapes) {
-  CoarsePlan p;
-  if (flags & (MSDA_FLAG_COARSE_OFF | MSDA_FLAG_DETERMINISTIC)) return p;
-  if (!fast_ok(d, dtype, flags)) return p;
-  if (!(d.D == 32 || d.D == 64 || d.D == 128)) return p;
-  // Opt-in: measured SLOWER than the all-reds backward at every benchmark shape: a
-  // shared-memory read-modify-write costs the SM's load/store pipe two instructions per 128-byte row where a vector
-  // red costs one, and the resident tile takes the L1 capacity the main kernel's gathers live on.
-  if (!(flags & MSDA_FLAG_COARSE_ON)) return p;
-  const int es = dtype == MSDA_BF16 ? 2 : 4;
-  int cap = 227 * 1024 - 1024 - d.D * 4 - 2 * msda::coarse_stage_bytes(d.D, es, d.L, d.P);
-  if (cap > kCoarseBudget) cap = kCoarseBudget;
-  if (cap < d.D * 4) return p;
-  if (host_shapes) {
-    int Hs[msda::kFastMaxLevels], Ws[msda::kFastMaxLevels];
-    for (int l = 0; l < d.L; ++l) {
-      Hs[l] = (int)host_shapes[2 * l];
-      Ws[l] = (int)host_shapes[2 * l + 1];
-    }
-    const int lc = msda::coarse_first_level(Hs, Ws, d.L, d.D, cap);
-    int64_t bytes = 0;
-    for (int l = lc; l < d.L; ++l) bytes += (int64_t)Hs[l] * Ws[l] * d.D * 4;
-    if (bytes == 0) return p;                       // nothing fits
-    p.budget = (int)bytes;
-    p.exact = true;
-    return p;
+// Test hook (msda_debug_bookkeeping with MSDA_DEBUG_FAST_RECORDS): builds the SAME PointRec the fast kernels build
+// (msda::make_record: locate + clamp + alias flags) and decodes it the way their gather loops do -- o00 = oc & ~15,
+// +H*D if bit0, +W_l*H*D if bit1; corner validity as the backward's finalize step derives it from bits 2/3 -- so
+// the integers the fast kernels actually gather from / scatter to are what the test compares bit for bit.
+__global__ void msda_fast_records_kernel(const float* __restrict__ loc, const int64_t* __restrict__ shapes,
+                                         const int64_t* __restrict__ lsi, int S, int H, int D, int L, int Q, int P,
+                                         int64_t npts, int64_t* __restrict__ offs, float* __restrict__ frac) {
+  const int HD = H * D;
+  for (int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pt < npts; pt += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)((pt / P) % L);
+    const int64_t row = pt / P / L;
+    const int h = (int)(row % H);
+    const int64_t b = row / H / Q;
+    const int Hl = (int)shapes[2 * l], Wl = (int)shapes[2 * l + 1];
+    const msda::PointRec r = msda::make_record(loc[2 * pt], loc[2 * pt + 1], 1.0f, Hl, Wl, (int)lsi[l], H, h, D);
+    const bool gated = r.lw < 0.0f;
+    const int oc = r.oc;
+    const int o00 = oc & ~15;
+    const int o01 = o00 + ((oc & 1) ? HD : 0);
+    const int dy = (oc & 2) ? Wl * HD : 0;
+    const bool x0v = (oc & 4) != 0, y0v = (oc & 8) != 0;
+    const bool x1v = (oc & 1) != 0 || !x0v, y1v = (oc & 2) != 0 || !y0v;
+    const int64_t img = b * (int64_t)S * HD;
+    offs[4 * pt + 0] = (!gated && x0v && y0v) ? img + o00 : -1;
+    offs[4 * pt + 1] = (!gated && x1v && y0v) ? img + o01 : -1;
+    offs[4 * pt + 2] = (!gated && x0v && y1v) ? img + o00 + dy : -1;
+    offs[4 * pt + 3] = (!gated && x1v && y1v) ? img + o01 + dy : -1;
+    frac[2 * pt] = gated ? 0.0f : r.lw;
+    frac[2 * pt + 1] = gated ? 0.0f : r.lh;
   }
-  const int64_t whole = (int64_t)d.S * d.D * 4;
-  p.budget = (int)(whole < cap ? whole : cap);
-  return p;
-}
-
-int bwd_coarse(cudaStream_t st, const Dims& d, int dtype, const void* go, const int64_t* shapes, const int64_t* lsi,
-               const void* loc, const void* w, float* gv, int budget) {
-  static const int exp_skip = exp_env("MSDA_EXP_SKIP_COARSE_KERNEL");
-  if (exp_skip) return MSDA_OK;
-  MSDA_CUDA(msda::launch_bwd_coarse(st, dtype == MSDA_BF16, go, shapes, lsi, (const float*)loc, (const float*)w, gv, d.B,
-                                    d.S, d.H, d.D, d.L, d.Q, d.P, budget));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return MSDA_OK;
-}
-
-// The coarse kernel (1 CTA per SM, most of the SM's shared memory, few warps) and the fast kernel (many small
-// CTAs) use different resources, so they run CONCURRENTLY: the coarse kernel goes first on a library-owned
-// high-priority side stream, the fast kernel fills the rest of every SM from the caller's stream, and the
-// caller's stream then waits for the side stream.  One side stream + event pair per device, created on first
-// use; the fork/join is enqueued under a mutex (cudaStreamWaitEvent binds to the record that precedes it, so
-// re-using the events afterwards is safe).
-struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-};
-constexpr int kMaxDevices = 64;
-SideStream g_side[kMaxDevices];
-std::mutex g_side_mutex;
-
-cudaError_t side_stream(SideStream** out) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
-  SideStream& s = g_side[dev];
-  if (!s.stream) {
-    int lo = 0, hi = 0;
-    e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, hi);
-    if (e != cudaSuccess) return e;
-    e = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
-    if (e != cudaSuccess) return e;
-    e = cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming);
-    if (e != cudaSuccess) return e;
-  }
-  *out = &s;
-  return cudaSuccess;
-}
-
-// fast backward + coarse accumulation, concurrent unless the caller's stream is being captured into a graph
-// (or MSDA_FLAG_COARSE_SERIAL): then both run on the caller's stream, one after the other
-int bwd_fast_with_coarse(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* go, const void* value,
-                         const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, float* gv, void* gl,
-                         void* gw, int budget, bool exact) {
-  bool serial = (flags & MSDA_FLAG_COARSE_SERIAL) != 0 || !exact;
-  if (!serial) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    MSDA_CUDA(cudaStreamIsCapturing(st, &cs));
-    serial = cs != cudaStreamCaptureStatusNone;
-  }
-  if (serial) {
-    if (int s = bwd_fast(st, d, dtype, flags, go, value, shapes, lsi, loc, w, gv, gl, gw, budget)) return s;
-    return bwd_coarse(st, d, dtype, go, shapes, lsi, loc, w, gv, budget);
-  }
-  std::lock_guard<std::mutex> lock(g_side_mutex);
-  SideStream* side = nullptr;
-  MSDA_CUDA(side_stream(&side));
-  MSDA_CUDA(cudaEventRecord(side->fork, st));            // after the caller's zero-fill of grad_value
-  MSDA_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-  int s = bwd_coarse(side->stream, d, dtype, go, shapes, lsi, loc, w, gv, budget);
-  if (s == MSDA_OK) s = bwd_fast(st, d, dtype, flags, go, value, shapes, lsi, loc, w, gv, gl, gw, budget);
-  // join even after a failure so the caller's stream never runs ahead of work already queued on the side stream
-  cudaError_t e = cudaEventRecord(side->join, side->stream);
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, side->join, 0);
-  if (s != MSDA_OK) return s;
-  if (e != cudaSuccess) return cuda_fail(e, "joining the coarse-level side stream");
-  return MSDA_OK;
-}
-
-// deterministic accumulate: LINEAR order only
-int bwd_fast_det(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
-                 const int64_t* lsi, const void* loc, const void* w, unsigned long long* acc, void* gl, void* gw,
-                 const msda::DetScale* det) {
-  const unsigned flags = MSDA_FLAG_ORDER_LINEAR;
-#define CALL_BWD(D_, VT_, PT_, TH_, TL_)                                                                      \
-  launch_bwd_fast<D_, VT_, PT_, kBwdThreads, 0, unsigned long long>(st, d, go, value, shapes, lsi, loc, w, acc, gl, \
-                                                                gw, det)
-  if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
-  MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
-#undef CALL_BWD
-}
-
-// sorted deterministic path: backward without the scatter (grad_loc / grad_w only), LINEAR order
-int bwd_fast_noscatter(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value,
-                       const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, void* gl, void* gw) {
-  const unsigned flags = MSDA_FLAG_ORDER_LINEAR;
-#define CALL_BWD(D_, VT_, PT_, TH_, TL_)                                                                       \
-  launch_bwd_fast<D_, VT_, PT_, kBwdThreads, 0, msda::NoScatter>(st, d, go, value, shapes, lsi, loc, w,                  \
-                                                         (msda::NoScatter*)nullptr, gl, gw, nullptr)
-  if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
-  MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
-#undef CALL_BWD
 }
 
 template <typename VT>
@@ -480,7 +136,7 @@ int det_gather(cudaStream_t st, const Dims& d, const void* go, const int4* entri
     default: return fail(MSDA_ERR_UNSUPPORTED, "det gather: D=%d", d.D);
   }
 #undef CALL_G
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  count_launch();
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
 }
@@ -507,7 +163,7 @@ int det_cell_reduce(cudaStream_t st, const Dims& d, const void* go, const int4* 
     default: return fail(MSDA_ERR_UNSUPPORTED, "det cell reduce: D=%d", d.D);
   }
 #undef CALL_G
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  count_launch();
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
 }
@@ -543,82 +199,6 @@ bool det_sorted_ok(const Dims& d, int dtype, unsigned flags) {
   return (int64_t)d.B * d.H * msda::det_cells_bound(d.S, d.L) < lim && d.n_points() < lim && d.rows() < lim;
 }
 
-// fused pre-op chain: single-pass row orders only (LINEAR forward, STRIP backward)
-#define MSDA_DISPATCH_PT_FUSED(D_, VT_, CALL)     \
-  do {                                            \
-    if (d.P == 4) return CALL(D_, VT_, 4);        \
-    if (d.P == 8) return CALL(D_, VT_, 8);        \
-    return CALL(D_, VT_, 0);                      \
-  } while (0)
-#ifdef MSDA_EXP_SLIM
-#define MSDA_DISPATCH_D_FUSED(VT_, CALL) return fail(MSDA_ERR_UNSUPPORTED, "slim build: no fused kernels")
-#else
-#define MSDA_DISPATCH_D_FUSED(VT_, CALL)                     \
-  do {                                                       \
-    switch (d.D) {                                           \
-      case 16: MSDA_DISPATCH_PT_FUSED(16, VT_, CALL);        \
-      case 32: MSDA_DISPATCH_PT_FUSED(32, VT_, CALL);        \
-      case 64: MSDA_DISPATCH_PT_FUSED(64, VT_, CALL);        \
-      case 128: MSDA_DISPATCH_PT_FUSED(128, VT_, CALL);      \
-      default: return fail(MSDA_ERR_UNSUPPORTED, "fused path: D=%d", d.D); \
-    }                                                        \
-  } while (0)
-#endif
-
-int fwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* value, const int64_t* shapes, const int64_t* lsi,
-              const void* off, const void* logits, void* out, msda::FusedArgs fa) {
-#define CALL_FF(D_, VT_, PT_) launch_fwd_fast<D_, VT_, PT_, kFwdThreads, 0, msda::kPreFused>(st, d, value, shapes, lsi, off, logits, out, fa)
-  if (dtype == MSDA_F32) MSDA_DISPATCH_D_FUSED(float, CALL_FF);
-  MSDA_DISPATCH_D_FUSED(__nv_bfloat16, CALL_FF);
-#undef CALL_FF
-}
-
-int bwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
-              const int64_t* lsi, const void* off, const void* logits, float* gv, void* goff, void* glog,
-              msda::FusedArgs fa) {
-#define CALL_FB(D_, VT_, PT_)                                                                                    \
-  launch_bwd_fast<D_, VT_, PT_, kBwdThreads, 2, float, msda::kPreFused>(st, d, go, value, shapes, lsi, off, logits, gv, goff, glog, \
-                                                     nullptr, fa)
-  if (dtype == MSDA_F32) MSDA_DISPATCH_D_FUSED(float, CALL_FB);
-  MSDA_DISPATCH_D_FUSED(__nv_bfloat16, CALL_FB);
-#undef CALL_FB
-}
-
-// DCNv3: runtime point count (K = kernel_h * kernel_w), LINEAR forward, STRIP backward
-#ifdef MSDA_EXP_SLIM
-#define MSDA_DISPATCH_D_DCN(VT_, CALL) return fail(MSDA_ERR_UNSUPPORTED, "slim build: no DCNv3 kernels")
-#else
-#define MSDA_DISPATCH_D_DCN(VT_, CALL)                       \
-  do {                                                       \
-    switch (d.D) {                                           \
-      case 16: return CALL(16, VT_);                         \
-      case 32: return CALL(32, VT_);                         \
-      case 64: return CALL(64, VT_);                         \
-      case 128: return CALL(128, VT_);                       \
-      default: return fail(MSDA_ERR_UNSUPPORTED, "dcnv3: group_channels=%d", d.D); \
-    }                                                        \
-  } while (0)
-#endif
-
-int fwd_dcn(cudaStream_t st, const Dims& d, int dtype, const void* input, const void* off, const void* mask, void* out,
-            msda::FusedArgs fa) {
-#define CALL_DF(D_, VT_) \
-  launch_fwd_fast<D_, VT_, 0, kFwdThreads, 0, msda::kPreDcn>(st, d, input, nullptr, nullptr, off, mask, out, fa)
-  if (dtype == MSDA_F32) MSDA_DISPATCH_D_DCN(float, CALL_DF);
-  MSDA_DISPATCH_D_DCN(__nv_bfloat16, CALL_DF);
-#undef CALL_DF
-}
-
-int bwd_dcn(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* input, const void* off,
-            const void* mask, float* gi, void* goff, void* gmask, msda::FusedArgs fa) {
-#define CALL_DB(D_, VT_)                                                                                          \
-  launch_bwd_fast<D_, VT_, 0, kBwdThreads, 2, float, msda::kPreDcn>(st, d, go, input, nullptr, nullptr, off, mask, gi, goff, \
-                                                            gmask, nullptr, fa)
-  if (dtype == MSDA_F32) MSDA_DISPATCH_D_DCN(float, CALL_DB);
-  MSDA_DISPATCH_D_DCN(__nv_bfloat16, CALL_DB);
-#undef CALL_DB
-}
-
 // ------------------------------------------------------------------------------------------
 // generic launches
 // ------------------------------------------------------------------------------------------
@@ -630,7 +210,7 @@ int fwd_generic(cudaStream_t st, const Dims& d, const void* value, const int64_t
   msda::msda_fwd_generic_kernel<VT, CT><<<grid, 256, 0, st>>>((const VT*)value, shapes, lsi, (const CT*)loc,
                                                               (const CT*)w, (VT*)out, d.S, d.H, d.D, d.L, d.Q, d.P,
                                                               total);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  count_launch();
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
 }
@@ -646,7 +226,7 @@ int bwd_generic(cudaStream_t st, const Dims& d, const void* go, const void* valu
   msda::msda_bwd_generic_kernel<VT, CT, ACC><<<grid, threads, 0, st>>>(
       (const VT*)go, (const VT*)value, shapes, lsi, (const CT*)loc, (const CT*)w, gv, (CT*)gl, (CT*)gw, det, d.S, d.H,
       d.D, d.L, d.Q, d.P, rows);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  count_launch();
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
 }
@@ -739,16 +319,6 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
                   int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
                   void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
                   size_t workspace_bytes, int dtype, unsigned flags) {
-  return msda_backward_hs(stream, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                          batch, spatial_size, num_heads, channels, num_levels, num_query, num_point, grad_value,
-                          grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes, dtype, flags, nullptr);
-}
-
-int msda_backward_hs(void* stream, const void* grad_output, const void* value, const int64_t* spatial_shapes,
-                     const int64_t* level_start_index, const void* sampling_loc, const void* attn_weight, int batch,
-                     int spatial_size, int num_heads, int channels, int num_levels, int num_query, int num_point,
-                     void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
-                     size_t workspace_bytes, int dtype, unsigned flags, const int64_t* spatial_shapes_host) {
   g_err[0] = 0;
   const Dims d{batch, spatial_size, num_heads, channels, num_levels, num_query, num_point};
   if (int s = check_dims(d, dtype)) return s;
@@ -792,7 +362,7 @@ int msda_backward_hs(void* stream, const void* grad_output, const void* value, c
                                                     num_point, dtype, flags);
   if (need && (!workspace || workspace_bytes < need))
     return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, workspace_bytes);
-  auto count = [] { g_launches.fetch_add(1, std::memory_order_relaxed); };
+  auto count = [] { count_launch(); };
 
   if (det) {
     // ---- bit-reproducible grad_value: 64-bit fixed-point accumulation (see include/msda.h) ----
@@ -901,13 +471,12 @@ int msda_backward_hs(void* stream, const void* grad_output, const void* value, c
 
   int s;
   if (fast_ok(d, dtype, flags)) {
-    const CoarsePlan plan = coarse_plan(d, dtype, flags, spatial_shapes_host);
-    if (plan.budget > 0)
-      s = bwd_fast_with_coarse(st, d, dtype, flags, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
-                               attn_weight, gv32, grad_sampling_loc, grad_attn_weight, plan.budget, plan.exact);
+    if (fold_applies(d, dtype, flags))
+      s = bwd_fold(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, gv32,
+                   grad_sampling_loc, grad_attn_weight, nullptr);
     else
       s = bwd_fast(st, d, dtype, flags, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
-                   attn_weight, gv32, grad_sampling_loc, grad_attn_weight, 0);
+                   attn_weight, gv32, grad_sampling_loc, grad_attn_weight);
   } else if (dtype == MSDA_F32) {
     s = bwd_generic<float, float, float>(st, d, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
                                          attn_weight, gv32, grad_sampling_loc, grad_attn_weight);
@@ -957,6 +526,7 @@ int msda_fused_forward(void* stream, const void* value, const int64_t* spatial_s
   fa.ref = reference_points;
   fa.ref_dim = ref_dim;
   fa.inv_P = 1.0f / (float)num_point;
+  fa.num_P = (float)num_point;
   fa.value_mask = value_padding_mask;
   return fwd_fused(static_cast<cudaStream_t>(stream), d, dtype, value, spatial_shapes, level_start_index,
                    sampling_offsets, attn_logits, output, fa);
@@ -992,15 +562,21 @@ int msda_fused_backward(void* stream, const void* grad_output, const void* value
   fa.ref = reference_points;
   fa.ref_dim = ref_dim;
   fa.inv_P = 1.0f / (float)num_point;
+  fa.num_P = (float)num_point;
   fa.value_mask = value_padding_mask;
-  if (int s = bwd_fused(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_offsets,
-                        attn_logits, gv32, grad_offsets, grad_logits, fa))
-    return s;
+  int s;
+  if (fold_applies(d, dtype, flags))
+    s = bwd_fold(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                 gv32, grad_offsets, grad_logits, &fa);
+  else
+    s = bwd_fused(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                  gv32, grad_offsets, grad_logits, fa);
+  if (s != MSDA_OK) return s;
   if (dtype == MSDA_BF16) {
     const int64_t n = d.n_value();
     msda::msda_cast_f32_to_bf16_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
         gv32, static_cast<__nv_bfloat16*>(grad_value), n);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch();
     MSDA_CUDA(cudaGetLastError());
   }
   return MSDA_OK;
@@ -1097,7 +673,7 @@ int msda_dcnv3_backward(void* stream, const void* grad_output, const void* input
     const int64_t n = d.n_value();
     msda::msda_cast_f32_to_bf16_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
         gi32, static_cast<__nv_bfloat16*>(grad_input), n);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    count_launch();
     MSDA_CUDA(cudaGetLastError());
   }
   return MSDA_OK;
@@ -1115,10 +691,15 @@ int msda_debug_bookkeeping(void* stream, const float* sampling_loc, const int64_
   DeviceGuard guard;
   MSDA_CUDA(guard.enter(sampling_loc));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  msda::msda_bookkeeping_kernel<<<grid_for(d.n_points(), 256, 148 * 16), 256, 0, st>>>(
-      sampling_loc, spatial_shapes, level_start_index, d.S, d.H, d.D, d.L, d.Q, d.P, d.n_points(), corner_offsets,
-      frac);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (fast_ok(d, MSDA_F32, 0))   // what the fast kernels index with (their own records, decoded)
+    msda_fast_records_kernel<<<grid_for(d.n_points(), 256, 148 * 16), 256, 0, st>>>(
+        sampling_loc, spatial_shapes, level_start_index, d.S, d.H, d.D, d.L, d.Q, d.P, d.n_points(), corner_offsets,
+        frac);
+  else
+    msda::msda_bookkeeping_kernel<<<grid_for(d.n_points(), 256, 148 * 16), 256, 0, st>>>(
+        sampling_loc, spatial_shapes, level_start_index, d.S, d.H, d.D, d.L, d.Q, d.P, d.n_points(), corner_offsets,
+        frac);
+  count_launch();
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;
 }

@@ -13,14 +13,14 @@
 // then broadcast-read by all lanes of the row in the gather loop.
 //
 // Row order (which rows a CTA works on; results never depend on it):
-//   LINEAR  rows in memory order (b, q, h): a CTA pass = THREADS/LANES consecutive rows.
-//   TILED   for encoder self-attention (Q == S, query i IS pixel i of the level pyramid): a
-//           persistent CTA walks work items (image, query tile, head) where a query tile is a
-//           TW x TH block of pixels of ONE level and ONE head.  Neighbouring queries sample
-//           neighbouring pixels, so the tile's gather footprint (~100 KB for 16x8 queries x 4
-//           levels, fp32) stays in the SM's L1 instead of being re-fetched from L2 per query row.
-//           The tile table is derived in-kernel from the DEVICE spatial_shapes, so no host copy of
-//           the shapes (and no sync) is needed and any grid size is correct.
+//   LINEAR  rows in memory order (b, q, h): a CTA = THREADS/LANES consecutive rows.
+//   STRIP   a CTA = THREADS/LANES consecutive queries of ONE head (any Q).
+//   TILE2D  encoder self-attention only (Q == S, query i IS pixel i of the level pyramid): a CTA = a
+//           TW x TH block of pixels of ONE level and ONE head.  The tile table is derived in-kernel from the
+//           DEVICE spatial_shapes, so no host copy of the shapes (and no sync) is needed.
+// (Round 1 also carried a persistent 1024-thread TILED order, a head-major STRIP variant and a shared-memory
+// accumulation of the coarse levels; all three were measured slower -- profiles/r01*_experiments.txt, DESIGN.md
+// section 6 -- and were removed from the library in round 2.)
 //
 // Backward: per point each lane forms 4 partial dot products <grad_out, corner_k> over its 4
 // channels; partials of 4 points are transposed-and-reduced across the row's lanes with a
@@ -140,33 +140,14 @@ struct LevelTab {
   int H[kFastMaxLevels];
   int W[kFastMaxLevels];
   int start[kFastMaxLevels];
-  int tiles_x[kFastMaxLevels];     // TILED only
-  int tile_begin[kFastMaxLevels];  // TILED only: first tile index of the level
-  int total_tiles;                 // TILED only
-  int first_coarse;                // backward: levels >= this one accumulate grad_value in msda_coarse.cuh, not here
-  int pad[2];
+  int tiles_x[kFastMaxLevels];     // tile orders only
+  int tile_begin[kFastMaxLevels];  // tile orders only: first tile index of the level
+  int total_tiles;                 // tile orders only
+  int pad[3];
 };
 
-// Backward, shared-memory accumulation of the coarse levels (msda_coarse.cuh): the resident levels are the
-// longest suffix of the pyramid (at most kCoarseMaxLevels) whose pixels x D floats fit in `budget_bytes`.
-// Returns the first resident level, L when nothing fits (or budget == 0: every level goes through reds).
-// Evaluated on the device by both kernels from the same inputs, so they always agree (the host evaluates it too,
-// when it has a copy of the shapes, to size the tile exactly: budget = the resident levels' bytes).
-constexpr int kCoarseMaxLevels = 4;
-__host__ __device__ __forceinline__ int coarse_first_level(const int* Hs, const int* Ws, int L, int D, int budget_bytes) {
-  int lc = L;
-  long long acc = 0;
-  for (int l = L - 1; l >= 0 && L - l <= kCoarseMaxLevels; --l) {
-    acc += (long long)Hs[l] * Ws[l] * D * 4;
-    if (acc > (long long)budget_bytes) break;
-    lc = l;
-  }
-  return lc;
-}
-
 template <int TW, int TH>
-__device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes, const int64_t* lsi, int L, int D = 0,
-                                            int coarse_budget = 0) {
+__device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes, const int64_t* lsi, int L) {
   if (threadIdx.x < L) {
     tab->H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
     tab->W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
@@ -182,12 +163,11 @@ __device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes
       acc += tx * ty;
     }
     tab->total_tiles = acc;
-    tab->first_coarse = coarse_budget > 0 ? coarse_first_level(tab->H, tab->W, L, D, coarse_budget) : L;
   }
   __syncthreads();
 }
 
-// LINEAR / STRIP orders need no tile table: one barrier, no serial section (first_coarse is left to the caller)
+// LINEAR / STRIP orders need no tile table: one barrier, no serial section
 __device__ __forceinline__ void load_levels_plain(LevelTab* tab, const int64_t* shapes, const int64_t* lsi, int L) {
   if (threadIdx.x < L) {
     tab->H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
@@ -207,7 +187,6 @@ __device__ __forceinline__ void set_single_level(LevelTab* tab, int H, int W) {
     tab->tiles_x[0] = (W + TW - 1) / TW;
     tab->tile_begin[0] = 0;
     tab->total_tiles = tab->tiles_x[0] * ((H + TH - 1) / TH);
-    tab->first_coarse = 1;
   }
   __syncthreads();
 }
@@ -236,119 +215,63 @@ struct RowRef {
   bool live;
 };
 
-// ---- asynchronous staging of a row's raw locations / weights (global -> shared, no registers) ----
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+// shared-memory words per row (host and device must agree)
+__host__ __device__ constexpr int fwd_row_words(int NP) {
+  // float4 cw[NP] | int oc[NP] | pad
+  return ((((5 * NP + 1) & ~1) + 3) & ~3) + 4;
 }
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// shared-memory words per row (host and device must agree).  STAGED adds the raw loc/w buffers of
-// the persistent (TILED) kernels' cp.async pipeline.
-__host__ __device__ constexpr int fwd_row_words(int NP, bool staged) {
-  // float4 cw[NP] | int oc[NP] | [float2 raw_xy[NP] (8-byte aligned) | float raw_w[NP]] | pad
-  return (((((5 * NP + 1) & ~1) + (staged ? 3 * NP : 0)) + 3) & ~3) + 4;
-}
-__host__ __device__ constexpr int bwd_row_words(int NP, bool staged) {
-  // float4 cw[NP] | int4 fin[NP] | [float2 raw_xy[NP] | float raw_w[NP]] | pad
-  return ((8 * NP + (staged ? 3 * NP : 0) + 3) & ~3) + 4;
-}
-
-template <int LANES>
-__device__ __forceinline__ void stage_row(float2* raw_xy, float* raw_w, const float* loc, const float* w,
-                                          const RowRef& rr, int NP, int sub) {
-  if (rr.live) {
-    const float2* lp = reinterpret_cast<const float2*>(loc + rr.row * (int64_t)NP * 2);
-    const float* wp = w + rr.row * (int64_t)NP;
-    for (int pt = sub; pt < NP; pt += LANES) {
-      cp_async8(raw_xy + pt, lp + pt);
-      cp_async4(raw_w + pt, wp + pt);
-    }
-  }
+__host__ __device__ constexpr int bwd_row_words(int NP) {
+  // float4 cw[NP] | int4 fin[NP] | pad
+  return 8 * NP + 4;
 }
 
 // Row iterator: yields this thread's row for every work item of the CTA.
-// ORDER: 0 = LINEAR, 1 = TILED (persistent grid-stride), 2 = STRIP (one CTA = RPC consecutive queries
-// of ONE head; x-adjacent queries of a head share bilinear corners, so the CTA re-uses lines in L1 --
-// needs no knowledge of the level shapes and works for any Q), 3 = TILE2D (encoder form, Q == S: one CTA =
-// a TW x TH pixel tile of one level and ONE head, tile index slowest; the grid is an upper bound computed
-// from S alone -- surplus CTAs exit, a grid-stride step covers pathological pyramids -- so the level shapes
-// never have to be known on the host).
+// ORDER: 0 = LINEAR, 2 = STRIP (one CTA = RPC consecutive queries of ONE head; x-adjacent queries of a head share
+// bilinear corners, so the CTA re-uses lines in L1 -- needs no knowledge of the level shapes and works for any Q),
+// 3 = TILE2D (encoder form, Q == S: one CTA = a TW x TH pixel tile of one level and ONE head, tile index
+// slowest; the grid is an upper bound computed from S alone -- surplus CTAs exit, a grid-stride step covers
+// pathological pyramids -- so the level shapes never have to be known on the host).  (1 was round 1's TILED.)
 template <int D, int THREADS, int ORDER>
 struct RowWalk {
+  static_assert(ORDER == 0 || ORDER == 2 || ORDER == 3, "row orders: LINEAR, STRIP, TILE2D");
   using G = Geom<D, THREADS>;
   int64_t item, n_items, rows;
   int rin, BH;
-  bool head_major = false;   // STRIP only: items ordered (image, head, strip) instead of (image, strip, head)
   __device__ __forceinline__ RowWalk() {}
   // LINEAR / STRIP do not read `tab`, so they may start before the level table is loaded
   __device__ __forceinline__ RowWalk(const LevelTab* tab, int B, int H, int64_t rows_) : rows(rows_) {
     rin = threadIdx.x / G::LANES;
     item = blockIdx.x;
     BH = B * H;
-    if (ORDER == 1 || ORDER == 3) n_items = (int64_t)B * H * tab->total_tiles;
+    if (ORDER == 3) n_items = (int64_t)B * H * tab->total_tiles;
     else if (ORDER == 2) n_items = (int64_t)B * H * ((rows / ((int64_t)B * H) + G::RPC - 1) / G::RPC);
     else n_items = (rows + G::RPC - 1) / G::RPC;
   }
   __device__ __forceinline__ bool done() const { return item >= n_items; }
   // LINEAR / STRIP kernels are launched with one CTA per item: a single pass, no loop-carried state.
-  __device__ __forceinline__ void next() { item = (ORDER == 1 || ORDER == 3) ? item + gridDim.x : n_items; }
+  __device__ __forceinline__ void next() { item = (ORDER == 3) ? item + gridDim.x : n_items; }
   __device__ __forceinline__ RowRef get(const LevelTab* tab, int L, int H, int Q) const {
     RowRef r;
     if (ORDER == 2) {
       const int chunks = (Q + G::RPC - 1) / G::RPC;
-      int h, b, q;
-      if (head_major) {
-        // all strips of one (image, head) are adjacent in launch order, so at any moment (nearly) every CTA of
-        // an SM works on the SAME head: that head's coarse levels (35 + 134 KB at DINO-R50 800x1333) then stay
-        // in the SM's L1 and half of the corner gathers stop crossing the crossbar
-        const int64_t bh = item / chunks;
-        q = (int)(item - bh * chunks) * G::RPC + rin;
-        b = (int)(bh / H);
-        h = (int)(bh - (int64_t)b * H);
-      } else {
-        // item = blockIdx.x fits 32 bits: unsigned arithmetic instead of three 64-bit divisions per thread
-        const unsigned it = (unsigned)item, bc = it / (unsigned)H, bb = bc / (unsigned)chunks;
-        h = (int)(it - bc * (unsigned)H);
-        q = (int)(bc - bb * (unsigned)chunks) * G::RPC + rin;
-        b = (int)bb;
-      }
+      // item = blockIdx.x fits 32 bits: unsigned arithmetic instead of three 64-bit divisions per thread
+      const unsigned it = (unsigned)item, bc = it / (unsigned)H, bb = bc / (unsigned)chunks;
+      const int h = (int)(it - bc * (unsigned)H);
+      const int q = (int)(bc - bb * (unsigned)chunks) * G::RPC + rin;
+      const int b = (int)bb;
       r.live = q < Q;
       r.b = b;
       r.h = h;
       r.row = r.live ? ((int64_t)b * Q + q) * H + h : 0;
     } else if (ORDER == 3) {
       const unsigned it = (unsigned)item;
-      const unsigned t = it / (unsigned)BH, r = it - t * (unsigned)BH;
-      const int b = (int)(r / (unsigned)H), h = (int)(r - (unsigned)b * (unsigned)H);
+      const unsigned t = it / (unsigned)BH, rem = it - t * (unsigned)BH;
+      const int b = (int)(rem / (unsigned)H), h = (int)(rem - (unsigned)b * (unsigned)H);
       int l = 0;
 #pragma unroll 1
       for (int k = 1; k < L; ++k)
         if ((int)t >= tab->tile_begin[k]) l = k;
       const int tt = (int)t - tab->tile_begin[l];
-      const int ty = tt / tab->tiles_x[l], tx = tt - ty * tab->tiles_x[l];
-      const int y = ty * G::TH + rin / G::TW, x = tx * G::TW + rin % G::TW;
-      const int q = tab->start[l] + y * tab->W[l] + x;
-      RowRef rr;
-      rr.live = (y < tab->H[l]) && (x < tab->W[l]) && (q < Q);
-      rr.b = b;
-      rr.h = h;
-      rr.row = rr.live ? ((int64_t)b * Q + q) * H + h : 0;
-      return rr;
-    } else if (ORDER == 1) {
-      const int h = (int)(item % H);
-      const int64_t bt = item / H;
-      const int t = (int)(bt % tab->total_tiles);
-      const int b = (int)(bt / tab->total_tiles);
-      int l = 0;
-#pragma unroll 1
-      for (int k = 1; k < L; ++k)
-        if (t >= tab->tile_begin[k]) l = k;
-      const int tt = t - tab->tile_begin[l];
       const int ty = tt / tab->tiles_x[l], tx = tt - ty * tab->tiles_x[l];
       const int y = ty * G::TH + rin / G::TW, x = tx * G::TW + rin % G::TW;
       const int q = tab->start[l] + y * tab->W[l] + x;
@@ -443,7 +366,8 @@ struct FusedArgs {
   // kernels -- a masked pixel's row reads as zeros, see apply_value_mask
   const unsigned char* value_mask;
   int ref_dim;        // 2: loc = ref + off / (W_l, H_l);  4: loc = ref_xy + off / P * ref_wh * 0.5
-  float inv_P;        // 1 / P
+  float inv_P;        // 1 / P (backward chain rule)
+  float num_P;        // P as a float: the forward divides (torch computes off / P, not off * (1/P))
   // PRE == 2 (DCNv3): the same gather/scatter core driven by a convolution-style
   // sampling grid (detrex/layers/csrc/DCNv3/dcnv3_im2col_cuda.cuh:217-275): rows are (n, output pixel,
   // group), the K = kernel_w*kernel_h points of a row sit at
@@ -458,14 +382,14 @@ struct FusedArgs {
 constexpr int kPrePlain = 0, kPreFused = 1, kPreDcn = 2;
 
 __device__ __forceinline__ float2 fused_location(const float2 off, const float* r, int ref_dim, int Hl, int Wl,
-                                                 float inv_P) {
+                                                 float num_P) {
   float2 loc;
   if (ref_dim == 2) {
     loc.x = __fadd_rn(__ldg(r + 0), __fdiv_rn(off.x, (float)Wl));
     loc.y = __fadd_rn(__ldg(r + 1), __fdiv_rn(off.y, (float)Hl));
   } else {
-    loc.x = __fadd_rn(__ldg(r + 0), __fmul_rn(__fmul_rn(__fmul_rn(off.x, inv_P), __ldg(r + 2)), 0.5f));
-    loc.y = __fadd_rn(__ldg(r + 1), __fmul_rn(__fmul_rn(__fmul_rn(off.y, inv_P), __ldg(r + 3)), 0.5f));
+    loc.x = __fadd_rn(__ldg(r + 0), __fmul_rn(__fmul_rn(__fdiv_rn(off.x, num_P), __ldg(r + 2)), 0.5f));
+    loc.y = __fadd_rn(__ldg(r + 1), __fmul_rn(__fmul_rn(__fdiv_rn(off.y, num_P), __ldg(r + 3)), 0.5f));
   }
   return loc;
 }
@@ -532,32 +456,29 @@ __device__ __forceinline__ float row_softmax(const float* logits_row, float* scr
 // =============================================================================================
 // Forward
 // =============================================================================================
-// LINEAR / STRIP: one pass per CTA, phase 1 reads loc/w straight from global memory.
-// TILED (persistent): software pipeline per warp -- wait for this item's raw loc/w in shared memory
-//   -> phase 1: records -> issue cp.async for the NEXT item's loc/w -> phase 2: gather (the long
-//   phase, hides the HBM latency of the copy).
+// One pass per CTA (TILE2D: a grid-stride step for pathological pyramids); phase 1 reads loc/w straight from
+// global memory.
 template <int D, typename VT, int PT, int THREADS, int ORDER, int PRE, int CPL>
 #ifndef MSDA_FWD_MINB
 #define MSDA_FWD_MINB 6
 #endif
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256) ? MSDA_FWD_MINB * (256 / THREADS) : ((THREADS == 512) ? 3 : 1))
+__global__ void __launch_bounds__(THREADS, MSDA_FWD_MINB * (256 / THREADS))
 msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                      const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                      const float* __restrict__ w, VT* __restrict__ out, const FusedArgs fused, int B, int S, int H,
-                     int L, int Q, int P, int64_t rows, int head_major) {
+                     int L, int Q, int P, int64_t rows) {
   // FUSED: `loc` holds raw sampling offsets and `w` attention logits (see FusedArgs)
+  static_assert(THREADS <= 256, "single-pass CTAs");
   constexpr int DL = D * 4 / CPL;               // lane geometry: LANES = D / CPL lanes per row
   using G = Geom<DL, THREADS>;
   constexpr int LANES = G::LANES;
-  constexpr bool STAGED = (ORDER == 1);
   constexpr bool FUSED = (PRE == kPreFused);
   constexpr bool DCN = (PRE == kPreDcn);
-  static_assert(!(PRE != kPrePlain && STAGED), "the fused pre-op chains are built for the single-pass row orders");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
-  const int row_words = fwd_row_words(NP, STAGED);
+  const int row_words = fwd_row_words(NP);
 
   const int sub = (threadIdx.x & 31) % LANES;            // lane inside the row
   const int rin = threadIdx.x / LANES;                   // row inside the CTA
@@ -565,8 +486,6 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   float* my = recs + (size_t)rin * row_words;
   float4* s_cw = reinterpret_cast<float4*>(my);
   int* s_oc = reinterpret_cast<int*>(my + 4 * NP);
-  float2* raw_xy = reinterpret_cast<float2*>(my + ((5 * NP + 1) & ~1));
-  float* raw_w = my + ((5 * NP + 1) & ~1) + 2 * NP;
 
   // Single-pass orders (LINEAR, STRIP) know their row without the level table, so the first locations / weights
   // of the row are requested BEFORE the table's load + barrier: the two global-memory latencies of a CTA's
@@ -581,7 +500,6 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   RowRef cur;
   if constexpr (EARLY) {
     walk = RowWalk<DL, THREADS, ORDER>(tab, B, H, rows);
-    walk.head_major = head_major != 0;
     if (walk.done()) return;                             // uniform over the CTA
     cur = walk.get(tab, L, H, Q);
 #pragma unroll
@@ -599,21 +517,10 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
     else if constexpr (ORDER == 0 || ORDER == 2) load_levels_plain(tab, shapes, lsi, L);
     else load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
     walk = RowWalk<DL, THREADS, ORDER>(tab, B, H, rows);
-    walk.head_major = head_major != 0;
     if (walk.done()) return;
     cur = walk.get(tab, L, H, Q);
   }
-  if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
   while (true) {
-    bool has_next = false;
-    RowRef nxt = cur;
-    if constexpr (STAGED) {   // software pipeline: the next item is known (and its loc/w requested) early
-      walk.next();
-      has_next = !walk.done();
-      if (has_next) nxt = walk.get(tab, L, H, Q);
-      cp_async_wait_all();
-      __syncwarp();
-    }
     // ---- phase 1: records ----
     {
       const float2* lp = reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2);
@@ -627,7 +534,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
           const int l = level_of<PT>(pt, P);
           if constexpr (FUSED) {
             aw = __fdiv_rn(__int_as_float(s_oc[pt]), sm_sum);
-            xy = fused_location(xy, rp + l * fused.ref_dim, fused.ref_dim, tab->H[l], tab->W[l], fused.inv_P);
+            xy = fused_location(xy, rp + l * fused.ref_dim, fused.ref_dim, tab->H[l], tab->W[l], fused.num_P);
           }
           PointRec r;
           if constexpr (DCN) {
@@ -648,12 +555,10 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
           for (int i = 0; i < kEarly; ++i, pt += LANES)
             if (pt < NP) build(pt, early_xy[i], early_w[i]);
         }
-        for (; pt < NP; pt += LANES)
-          build(pt, STAGED ? raw_xy[pt] : __ldg(lp + pt), (STAGED && !FUSED) ? raw_w[pt] : (FUSED ? 0.0f : __ldg(wp + pt)));
+        for (; pt < NP; pt += LANES) build(pt, __ldg(lp + pt), FUSED ? 0.0f : __ldg(wp + pt));
       }
     }
     __syncwarp();
-    if (STAGED && has_next) stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
 
     // ---- phase 2: gather ----
     if (cur.live) {
@@ -683,16 +588,10 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
       }
       stv<CPL>(out + cur.row * D + sub * CPL, acc);
     }
-    if constexpr (STAGED) {
-      if (!has_next) break;
-      __syncwarp();   // records are rewritten by the next work item
-      cur = nxt;
-    } else {
-      walk.next();    // single-pass orders end here; TILE2D only continues for a pathological pyramid
-      if (walk.done()) break;
-      __syncwarp();
-      cur = walk.get(tab, L, H, Q);
-    }
+    walk.next();    // single-pass orders end here; TILE2D only continues for a pathological pyramid
+    if (walk.done()) break;
+    __syncwarp();
+    cur = walk.get(tab, L, H, Q);
   }
 }
 
@@ -815,28 +714,25 @@ __device__ __forceinline__ void transpose_reduce_4x4(float (&d)[16], int sub) {
 #define MSDA_BWD_MINB 4
 #endif
 template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC, int PRE, int CPL>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256) ? MSDA_BWD_MINB * (256 / THREADS) : 1)
+__global__ void __launch_bounds__(THREADS, MSDA_BWD_MINB * (256 / THREADS))
 msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ value,
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ w,
                      ACC* __restrict__ grad_value, float* __restrict__ grad_loc,
                      float* __restrict__ grad_w, const DetScale* __restrict__ det, const FusedArgs fused, int B,
-                     int S, int H, int L, int Q, int P, int64_t rows, int coarse_budget, int head_major) {
-  // coarse_budget > 0: grad_value of the levels that fit in that many bytes of shared memory is accumulated by
-  // msda_bwd_coarse_kernel (msda_coarse.cuh); this kernel then skips their reds (float accumulation only)
+                     int S, int H, int L, int Q, int P, int64_t rows) {
   // FUSED: loc = raw offsets, w = logits in; grad_loc = grad of the offsets, grad_w = grad of the logits out
+  static_assert(THREADS <= 256, "single-pass CTAs");
   constexpr int DL = D * 4 / CPL;
   using G = Geom<DL, THREADS>;
   constexpr int LANES = G::LANES;
-  constexpr bool STAGED = (ORDER == 1);
   constexpr bool FUSED = (PRE == kPreFused);
   constexpr bool DCN = (PRE == kPreDcn);
-  static_assert(!(PRE != kPrePlain && STAGED), "the fused pre-op chains are built for the single-pass row orders");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LevelTab* tab = reinterpret_cast<LevelTab*>(smem_raw);
   float* recs = reinterpret_cast<float*>(smem_raw + sizeof(LevelTab));
   const int NP = L * P;
-  const int row_words = bwd_row_words(NP, STAGED);
+  const int row_words = bwd_row_words(NP);
 
   const int sub = (threadIdx.x & 31) % LANES;
   const int rin = threadIdx.x / LANES;
@@ -844,8 +740,6 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   float* my = recs + (size_t)rin * row_words;
   float4* s_cw = reinterpret_cast<float4*>(my);
   int4* s_fin = reinterpret_cast<int4*>(my + 4 * NP);
-  float2* raw_xy = reinterpret_cast<float2*>(my + 8 * NP);
-  float* raw_w = my + 10 * NP;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   const float gscale = det ? det->scale : 1.0f;
 
@@ -863,7 +757,6 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   Vec<CPL> go = vzero<CPL>();
   if constexpr (EARLY) {
     walk = RowWalk<DL, THREADS, ORDER>(tab, B, H, rows);
-    walk.head_major = head_major != 0;
     if (walk.done()) return;                             // uniform over the CTA
     cur = walk.get(tab, L, H, Q);
     if (cur.live) go = ldv<CPL>(grad_out + cur.row * D + sub * CPL);
@@ -880,33 +773,13 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   } else {
     if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
     else if constexpr (ORDER == 0 || ORDER == 2) load_levels_plain(tab, shapes, lsi, L);
-    else load_levels<G::TW, G::TH>(tab, shapes, lsi, L, D, coarse_budget);
+    else load_levels<G::TW, G::TH>(tab, shapes, lsi, L);
     walk = RowWalk<DL, THREADS, ORDER>(tab, B, H, rows);
-    walk.head_major = head_major != 0;
     if (walk.done()) return;
     cur = walk.get(tab, L, H, Q);
   }
-  // points [0, red_points) scatter with reds here; the rest belongs to msda_bwd_coarse_kernel (opt-in)
-  int first_coarse = L;
-  if (!DCN && coarse_budget > 0) {
-    if constexpr (ORDER == 0 || ORDER == 2) first_coarse = coarse_first_level(tab->H, tab->W, L, D, coarse_budget);
-    else first_coarse = tab->first_coarse;
-  }
-  const int red_points = first_coarse * P;
-  if (STAGED) stage_row<LANES>(raw_xy, raw_w, loc, w, cur, NP, sub);
-  if (STAGED && cur.live) go = ldv<CPL>(grad_out + cur.row * D + sub * CPL);
   while (true) {
-    bool has_next = false;
-    RowRef nxt = cur;
-    if constexpr (STAGED) {
-      walk.next();
-      has_next = !walk.done();
-      if (has_next) nxt = walk.get(tab, L, H, Q);
-      cp_async_wait_all();
-      __syncwarp();
-    } else if constexpr (!EARLY) {
-      go = cur.live ? ldv<CPL>(grad_out + cur.row * D + sub * CPL) : vzero<CPL>();
-    }
+    if constexpr (!EARLY) go = cur.live ? ldv<CPL>(grad_out + cur.row * D + sub * CPL) : vzero<CPL>();
     const float* rp = FUSED ? fused.ref + (cur.row / H) * (int64_t)L * fused.ref_dim : nullptr;
     {
       const float2* lp = reinterpret_cast<const float2*>(loc + cur.row * (int64_t)NP * 2);
@@ -922,7 +795,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           const int l = level_of<PT>(pt, P);
           if constexpr (FUSED) {
             aw = __fdiv_rn(__int_as_float(s_fin[pt].w), sm_sum);
-            xy = fused_location(xy, rp + l * fused.ref_dim, fused.ref_dim, tab->H[l], tab->W[l], fused.inv_P);
+            xy = fused_location(xy, rp + l * fused.ref_dim, fused.ref_dim, tab->H[l], tab->W[l], fused.num_P);
           }
           PointRec r;
           if constexpr (DCN) {
@@ -950,20 +823,13 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         float2 xy = make_float2(0.f, 0.f);
         float aw = 0.0f;
         if (cur.live) {
-          xy = STAGED ? raw_xy[pt] : __ldg(lp + pt);
-          if constexpr (!FUSED) aw = STAGED ? raw_w[pt] : __ldg(wp + pt);
+          xy = __ldg(lp + pt);
+          if constexpr (!FUSED) aw = __ldg(wp + pt);
         }
         build(pt, xy, aw);
       }
     }
     __syncwarp();
-    Vec<CPL> go_next = vzero<CPL>();
-    if constexpr (STAGED) {
-      if (has_next) {
-        stage_row<LANES>(raw_xy, raw_w, loc, w, nxt, NP, sub);
-        if (nxt.live) go_next = ldv<CPL>(grad_out + nxt.row * D + sub * CPL);
-      }
-    }
 
     constexpr bool DET = sizeof(ACC) == 8;
     constexpr bool SCATTER = sizeof(ACC) != sizeof(NoScatter);
@@ -1021,7 +887,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             if (cw.y != 0.0f) scatter4_det<LANES>(gimg + o01, cw.y, go_s, gscale);
             if (cw.z != 0.0f) scatter4_det<LANES>(gimg + o10, cw.z, go_s, gscale);
             if (cw.w != 0.0f) scatter4_det<LANES>(gimg + o11, cw.w, go_s, gscale);
-          } else if (pt < red_points) {
+          } else {
             if (cw.x != 0.0f) scatterv<CPL, D / 2>(gsc + o00, cw.x, go_sc);
             if (cw.y != 0.0f) scatterv<CPL, D / 2>(gsc + o01, cw.y, go_sc);
             if (cw.z != 0.0f) scatterv<CPL, D / 2>(gsc + o10, cw.z, go_sc);
@@ -1092,17 +958,10 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         }
       }
     }
-    if constexpr (STAGED) {
-      if (!has_next) break;
-      __syncwarp();   // records are rewritten by the next work item
-      cur = nxt;
-      go = go_next;
-    } else {
-      walk.next();
-      if (walk.done()) break;
-      __syncwarp();
-      cur = walk.get(tab, L, H, Q);
-    }
+    walk.next();
+    if (walk.done()) break;
+    __syncwarp();
+    cur = walk.get(tab, L, H, Q);
   }
 }
 

@@ -212,7 +212,8 @@ __global__ void msda_det_finalize_kernel(const long long* __restrict__ acc, VT* 
     store_as<VT, typename Compute<VT>::type>(dst + i, (typename Compute<VT>::type)((double)acc[i] * inv));
 }
 
-// Test hook, see include/msda.h::msda_debug_bookkeeping.
+// Test hook, see include/msda.h::msda_debug_bookkeeping: generic-kernel flavour (locate<float> + the reference's
+// per-corner bounds tests).  The fast kernels' own records are dumped by msda_fast_records_kernel (msda_capi.cu).
 __global__ void msda_bookkeeping_kernel(const float* __restrict__ loc, const int64_t* __restrict__ shapes,
                                         const int64_t* __restrict__ lsi, int S, int H, int D, int L, int Q, int P,
                                         int64_t npts, int64_t* __restrict__ offs, float* __restrict__ frac) {

@@ -109,7 +109,8 @@ class DeformableEncoderLayer(nn.Module):
         # self_attn: key = value = query, key_padding_mask = query_key_padding_mask (transformer.py:152-167)
         query = self.attentions[0](query, None, None, None, query_pos=query_pos,
                                    key_padding_mask=query_key_padding_mask, reference_points=reference_points,
-                                   spatial_shapes=spatial_shapes, level_start_index=level_start_index)
+                                   spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                                   level_shapes=kwargs.get("level_shapes"))
         query = self.norms[0](query)
         query = self.ffns[0](query)
         return self.norms[1](query)

@@ -53,27 +53,6 @@ def _flags(backward: bool) -> int:
     return f
 
 
-# Host copies of spatial_shapes, keyed by the device tensor's identity (storage address, version counter, shape).
-# The first backward with a given shapes tensor pays one device->host copy (16 integers); every later call is
-# sync-free.  The copy only sizes launches (msda_backward_hs in include/msda.h), it never enters the arithmetic.
-_host_shapes_cache: dict = {}
-
-
-def _host_shapes(spatial_shapes: torch.Tensor):
-    """ctypes int64 array holding spatial_shapes, or None when it cannot be had without breaking a graph capture."""
-    key = (spatial_shapes.device, spatial_shapes.data_ptr(), spatial_shapes._version, tuple(spatial_shapes.shape))
-    hit = _host_shapes_cache.get(key)
-    if hit is None:
-        if torch.cuda.is_current_stream_capturing():
-            return None
-        flat = [int(x) for x in spatial_shapes.detach().cpu().reshape(-1).tolist()]
-        hit = (ctypes.c_int64 * len(flat))(*flat)
-        if len(_host_shapes_cache) > 256:
-            _host_shapes_cache.clear()
-        _host_shapes_cache[key] = hit
-    return hit
-
-
 def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr())
 
@@ -148,24 +127,21 @@ def _backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weigh
     skip_scatter = (not need_grad_value and B * S * D > 0 and Q * L * P > 0
                     and b"_fast_" in handle.msda_dispatch_name(D, L, P, S, H, tag, flags, 1))
     if skip_scatter:
-        status = handle.msda_backward_hs(
+        status = handle.msda_backward(
             ctypes.c_void_p(torch.cuda.current_stream(value.device).cuda_stream), _ptr(grad_output), _ptr(value),
             _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc), _ptr(attn_weight), B, S, H, D, L, Q, P,
             ctypes.c_void_p(0), _ptr(grad_loc), _ptr(grad_w), ctypes.c_void_p(0), 0, tag,
-            flags | _lib.FLAG_NO_GRAD_VALUE, ctypes.c_void_p(0))
+            flags | _lib.FLAG_NO_GRAD_VALUE)
         _lib.check(status, "ms_deform_attn_backward")
         return [None, grad_loc, grad_w]
     grad_value = torch.empty_like(value)
     ws_bytes = int(handle.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, tag, flags))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
     stream = torch.cuda.current_stream(value.device).cuda_stream
-    host_shapes = _host_shapes(spatial_shapes)
-    status = handle.msda_backward_hs(ctypes.c_void_p(stream), _ptr(grad_output), _ptr(value), _ptr(spatial_shapes),
-                                     _ptr(level_start_index), _ptr(sampling_loc), _ptr(attn_weight), B, S, H, D, L, Q, P,
-                                     _ptr(grad_value), _ptr(grad_loc), _ptr(grad_w),
-                                     _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, tag, flags,
-                                     ctypes.cast(host_shapes, ctypes.c_void_p) if host_shapes is not None
-                                     else ctypes.c_void_p(0))
+    status = handle.msda_backward(ctypes.c_void_p(stream), _ptr(grad_output), _ptr(value), _ptr(spatial_shapes),
+                                  _ptr(level_start_index), _ptr(sampling_loc), _ptr(attn_weight), B, S, H, D, L, Q, P,
+                                  _ptr(grad_value), _ptr(grad_loc), _ptr(grad_w),
+                                  _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, tag, flags)
     _lib.check(status, "ms_deform_attn_backward")
     return [grad_value if need_grad_value else None, grad_loc, grad_w]
 
@@ -211,17 +187,65 @@ def multi_scale_deformable_attn_pytorch(value: torch.Tensor, value_spatial_shape
 # fused module path: softmax + sampling-location arithmetic inside the kernels
 # ------------------------------------------------------------------------------------------------
 def fused_supported(value: torch.Tensor, num_levels: int, num_points: int) -> bool:
-    """True when the fused kernels cover this problem (fast-kernel shapes, float32 / bfloat16 value,
-    non-deterministic mode); otherwise the module composes the pre-op chain in PyTorch."""
+    """True when the fused kernels cover this problem (fast-kernel shapes, float32 / bfloat16 value);
+    otherwise the module composes the pre-op chain in PyTorch."""
     if not value.is_cuda or value.dtype not in (torch.float32, torch.bfloat16) or value.dim() != 4:
         return False
     _, S, H, D = value.shape
-    return bool(_lib.lib().msda_fused_supported(D, num_levels, num_points, S, H, _DTYPE_TAG[value.dtype],
-                                                _flags(True)))
+    return bool(_lib.lib().msda_fused_supported(D, num_levels, num_points, S, H, _DTYPE_TAG[value.dtype], _flags(False)))
 
 
 def _mask_ptr(mask) -> ctypes.c_void_p:
     return _ptr(mask) if mask is not None else ctypes.c_void_p(0)
+
+
+def _check_fused_inputs(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                        key_padding_mask):
+    """Everything the kernels trust (they read the shapes as int64 and index with B/H/Q/L/P as given): the same
+    checks _check_inputs makes for the plain operator (ms_deform_attn_cuda.cu:29-39), for the fused argument list."""
+    _require(value.is_cuda, "Not implemented on the CPU")
+    for name, t in (("value", value), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
+                    ("reference_points", reference_points), ("spatial_shapes", spatial_shapes),
+                    ("level_start_index", level_start_index)):
+        _require(t.is_cuda and t.device == value.device, f"{name} must be a CUDA tensor on {value.device}")
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+    _require(value.dim() == 4, "value must be [B, S, H, D]")
+    _require(value.dtype in (torch.float32, torch.bfloat16), f"unsupported value dtype {value.dtype} (float32, bfloat16)")
+    _require(sampling_offsets.dim() == 6 and sampling_offsets.shape[-1] == 2, "sampling_offsets must be [B, Q, H, L, P, 2]")
+    B, S, H, D = value.shape
+    Bq, Q, Hq, L, P, _ = sampling_offsets.shape
+    _require(Bq == B and Hq == H, "sampling_offsets batch / heads do not match value")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64,
+             "spatial_shapes / level_start_index must be int64")
+    _require(tuple(spatial_shapes.shape) == (L, 2) and tuple(level_start_index.shape) == (L,),
+             "spatial_shapes must be [L, 2] and level_start_index [L]")
+    _require(sampling_offsets.dtype == torch.float32 and attn_logits.dtype == torch.float32
+             and reference_points.dtype == torch.float32, "offsets / logits / reference_points must be float32")
+    _require(tuple(attn_logits.shape) == (B, Q, H, L * P), "attn_logits must be [B, Q, H, L*P]")
+    ref_dim = reference_points.shape[-1]
+    _require(tuple(reference_points.shape) == (B, Q, L, ref_dim) and ref_dim in (2, 4),
+             "reference_points must be [B, Q, L, 2 or 4]")
+    mask = None
+    if key_padding_mask is not None:
+        _require(key_padding_mask.dtype in (torch.bool, torch.uint8), "key_padding_mask must be bool or uint8")
+        _require(tuple(key_padding_mask.shape) == (B, S), "key_padding_mask must be [B, S]")
+        _require(key_padding_mask.is_cuda and key_padding_mask.device == value.device,
+                 f"key_padding_mask must be a CUDA tensor on {value.device}")
+        mask = key_padding_mask.contiguous()   # one byte per pixel either way; non-zero = padded
+    return (B, S, H, D, L, Q, P, ref_dim), mask
+
+
+def _fused_pre_ops(spatial_shapes, sampling_offsets, attn_logits, reference_points):
+    """The module's own composition (multi_scale_deform_attn.py:300-332): softmax over L*P and the location affine."""
+    B, Q, H, L, P, _ = sampling_offsets.shape
+    weights = attn_logits.softmax(-1).view(B, Q, H, L, P)
+    if reference_points.shape[-1] == 2:
+        normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
+        loc = reference_points[:, :, None, :, None, :] + sampling_offsets / normalizer[None, None, None, :, None, :]
+    else:
+        loc = (reference_points[:, :, None, :, None, :2]
+               + sampling_offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5)
+    return loc.contiguous(), weights.contiguous()
 
 
 class MSDeformAttnFusedFunction(Function):
@@ -232,31 +256,18 @@ class MSDeformAttnFusedFunction(Function):
     followed by MultiScaleDeformableAttnFunction, without materialising locations / weights or their
     gradients.  With ``key_padding_mask [B,S]`` (bool or uint8, True = padded) it is additionally equivalent
     to ``value.masked_fill(key_padding_mask[..., None, None], 0)`` in front of that (py:291-292): ``value`` is
-    passed unmasked, masked pixels read as zeros inside the kernels and receive a zero ``grad_value``."""
+    passed unmasked, masked pixels read as zeros inside the kernels and receive a zero ``grad_value``.
+
+    Deterministic mode (set_deterministic / torch.use_deterministic_algorithms): the forward is the same fused
+    kernel (it has no atomics); the backward materialises locations / weights with the module's own PyTorch
+    composition, runs the bit-reproducible unfused backward (MSDA_FLAG_DETERMINISTIC) and applies the chain
+    rule through softmax / affine in PyTorch -- every step run-to-run reproducible."""
 
     @staticmethod
     def forward(ctx, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
                 key_padding_mask=None):
-        B, S, H, D = value.shape
-        _, Q, _, L, P, _ = sampling_offsets.shape
-        for name, t in (("value", value), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
-                        ("reference_points", reference_points), ("spatial_shapes", spatial_shapes),
-                        ("level_start_index", level_start_index)):
-            _require(t.is_cuda and t.device == value.device, f"{name} must be a CUDA tensor on {value.device}")
-            _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
-        _require(sampling_offsets.dtype == torch.float32 and attn_logits.dtype == torch.float32
-                 and reference_points.dtype == torch.float32, "offsets / logits / reference_points must be float32")
-        _require(tuple(attn_logits.shape) == (B, Q, H, L * P), "attn_logits must be [B, Q, H, L*P]")
-        ref_dim = reference_points.shape[-1]
-        _require(tuple(reference_points.shape) == (B, Q, L, ref_dim) and ref_dim in (2, 4),
-                 "reference_points must be [B, Q, L, 2 or 4]")
-        mask = None
-        if key_padding_mask is not None:
-            _require(key_padding_mask.dtype in (torch.bool, torch.uint8), "key_padding_mask must be bool or uint8")
-            _require(tuple(key_padding_mask.shape) == (B, S), "key_padding_mask must be [B, S]")
-            _require(key_padding_mask.is_cuda and key_padding_mask.device == value.device,
-                     f"key_padding_mask must be a CUDA tensor on {value.device}")
-            mask = key_padding_mask.contiguous()   # one byte per pixel either way; non-zero = padded
+        (B, S, H, D, L, Q, P, ref_dim), mask = _check_fused_inputs(
+            value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, key_padding_mask)
         out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
         stream = torch.cuda.current_stream(value.device).cuda_stream
         status = _lib.lib().msda_fused_forward(
@@ -275,16 +286,40 @@ class MSDeformAttnFusedFunction(Function):
         B, S, H, D = value.shape
         _, Q, _, L, P, _ = sampling_offsets.shape
         ref_dim = reference_points.shape[-1]
+        _require(grad_output.is_cuda and grad_output.device == value.device, "grad_output must be a CUDA tensor")
+        _require(grad_output.dtype == value.dtype, "grad_output dtype must match value")
+        _require(grad_output.numel() == B * Q * H * D, "grad_output must be [B, Q, H*D]")
         grad_output = grad_output.contiguous()
+        flags = _flags(True)
+        mask = ctx.value_mask
+        need_ref = ctx.needs_input_grad[5]
+        if (flags & _lib.FLAG_DETERMINISTIC) or need_ref:
+            # Composition around the unfused backward: the deterministic mode, and the rare case of reference points
+            # that require grad (DINO detaches them) -- d loc / d ref is the identity on (x, y) and off / P * 0.5 on
+            # (w, h), taken from grad_sampling_loc itself so that boxes with w == 0 or h == 0 keep their (x, y) grad.
+            loc, weights = _fused_pre_ops(spatial_shapes, sampling_offsets, attn_logits, reference_points)
+            v = value if mask is None else value.masked_fill(mask.bool()[..., None, None], 0)
+            grad_value, g_loc, g_w = _backward(v, spatial_shapes, level_start_index, loc, weights, grad_output,
+                                               need_grad_value=ctx.needs_input_grad[0])
+            if grad_value is not None and mask is not None:
+                grad_value = grad_value.masked_fill(mask.bool()[..., None, None], 0)
+            g_w = g_w.view(B, Q, H, L * P)
+            w_flat = weights.view(B, Q, H, L * P)
+            grad_logits = w_flat * (g_w - (g_w * w_flat).sum(-1, keepdim=True))
+            if ref_dim == 2:
+                normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1).to(g_loc.dtype)
+                grad_off = g_loc / normalizer[None, None, None, :, None, :]
+            else:
+                grad_off = g_loc * (reference_points[:, :, None, :, None, 2:] * (0.5 / P))
+            grad_ref = None
+            if need_ref:
+                g_xy = g_loc.sum(dim=(2, 4))
+                grad_ref = g_xy if ref_dim == 2 else torch.cat(
+                    [g_xy, (g_loc * sampling_offsets * (0.5 / P)).sum(dim=(2, 4))], -1)
+            return grad_value, None, None, grad_off, grad_logits, grad_ref, None
         grad_value = torch.empty_like(value)
         grad_off = torch.empty_like(sampling_offsets)
         grad_logits = torch.empty_like(attn_logits)
-        flags = _flags(True)
-        # the fused kernels have no bit-reproducible backward: say so instead of quietly running the float reds
-        # (the module checks fused_supported(), which is False in deterministic mode, and composes the unfused op)
-        _require(not (flags & _lib.FLAG_DETERMINISTIC),
-                 "MSDeformAttnFusedFunction has no deterministic backward; use MultiScaleDeformableAttnFunction "
-                 "(module.fuse_pre_ops = False) under torch.use_deterministic_algorithms / set_deterministic")
         tag = _DTYPE_TAG[value.dtype]
         handle = _lib.lib()
         ws_bytes = int(handle.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, tag, flags))
@@ -292,24 +327,11 @@ class MSDeformAttnFusedFunction(Function):
         stream = torch.cuda.current_stream(value.device).cuda_stream
         status = handle.msda_fused_backward(
             ctypes.c_void_p(stream), _ptr(grad_output), _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
-            _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points), ref_dim, _mask_ptr(ctx.value_mask),
+            _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points), ref_dim, _mask_ptr(mask),
             B, S, H, D, L, Q, P, _ptr(grad_value), _ptr(grad_off), _ptr(grad_logits),
             _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, tag, flags)
         _lib.check(status, "msda_fused_backward")
-        grad_ref = None
-        if ctx.needs_input_grad[5]:
-            # d loc / d ref: identity on (x, y); for boxes additionally off / P * 0.5 on (w, h).  Rare path
-            # (DINO detaches its reference points), so it is composed from grad_offsets in PyTorch.
-            wh = torch.stack([spatial_shapes[:, 1], spatial_shapes[:, 0]], -1).to(grad_off.dtype)   # (W_l, H_l)
-            if ref_dim == 2:
-                grad_ref = (grad_off * wh[None, None, None, :, None, :]).sum(dim=(2, 4))
-            else:
-                scale = reference_points[:, :, None, :, None, 2:] * (0.5 / P)          # d loc / d off
-                g_loc = torch.where(scale != 0, grad_off / scale, torch.zeros_like(grad_off))
-                g_xy = g_loc.sum(dim=(2, 4))
-                g_wh = (g_loc * sampling_offsets * (0.5 / P)).sum(dim=(2, 4))
-                grad_ref = torch.cat([g_xy, g_wh], -1)
-        return grad_value, None, None, grad_off, grad_logits, grad_ref, None
+        return grad_value, None, None, grad_off, grad_logits, None, None
 
 
 def debug_bookkeeping(sampling_loc: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,

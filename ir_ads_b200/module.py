@@ -9,7 +9,10 @@ core op runs on the sm_100a kernels through :class:`MultiScaleDeformableAttnFunc
 What differs from the reference module:
   * no device->host synchronisation per call: the reference asserts
     ``(spatial_shapes[:,0]*spatial_shapes[:,1]).sum() == num_value`` on the device tensor every
-    forward (py:286); here the check runs once per distinct shapes tensor and is cached;
+    forward (py:286), which blocks the host; here the same check runs every forward too, but either on a HOST
+    copy of the shapes the caller already has (``level_shapes=[(H_l, W_l), ...]``, what
+    ``encoder.flatten_levels`` returns) or as an asynchronous device-side assert (``torch._assert_async``:
+    no sync, CUDA-graph capturable; a violation surfaces as a device-side assertion failure);
   * bfloat16 activations (autocast bf16) go to the bf16-value kernel with float32 sampling
     locations / weights instead of failing in the float-only dispatch; float16 is widened to
     float32 around the op exactly as the reference does (py:343, :355-356);
@@ -61,7 +64,6 @@ class MultiScaleDeformableAttention(nn.Module):
         self.attention_weights = nn.Linear(embed_dim, num_heads * num_levels * num_points)
         self.value_proj = nn.Linear(embed_dim, embed_dim)
         self.output_proj = nn.Linear(embed_dim, embed_dim)
-        self._shape_checks = {}
         # fused pre-op chain (softmax + sampling-location arithmetic inside the kernels); set False to
         # run the reference's step-by-step composition around the core op instead
         self.fuse_pre_ops = True
@@ -85,16 +87,20 @@ class MultiScaleDeformableAttention(nn.Module):
         nn.init.xavier_uniform_(self.output_proj.weight.data)
         nn.init.constant_(self.output_proj.bias.data, 0.0)
 
-    def _check_shapes_once(self, spatial_shapes: torch.Tensor, num_value: int) -> None:
-        key = (spatial_shapes.data_ptr(), spatial_shapes._version, tuple(spatial_shapes.shape), num_value)
-        if key in self._shape_checks:
+    @staticmethod
+    def _check_shapes(spatial_shapes: torch.Tensor, num_value: int, level_shapes=None) -> None:
+        """sum(H_l * W_l) == num_value (py:286).  The fast kernels' 32-bit offsets and the deterministic path's
+        workspace bound rely on it, so it is checked on every call -- never cached by tensor address."""
+        if level_shapes is not None:
+            total = sum(int(h) * int(w) for h, w in level_shapes)
+            if total != num_value or len(level_shapes) != spatial_shapes.shape[0]:
+                raise AssertionError(f"sum(H_l*W_l) = {total} does not match the value length {num_value}")
             return
-        total = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum())  # one sync per distinct tensor
-        if total != num_value:
-            raise AssertionError(f"sum(H_l*W_l) = {total} does not match the value length {num_value}")
-        if len(self._shape_checks) > 64:
-            self._shape_checks.clear()
-        self._shape_checks[key] = True
+        ok = (spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum() == num_value
+        if spatial_shapes.is_cuda:
+            torch._assert_async(ok)          # no host sync; capturable
+        elif not bool(ok):
+            raise AssertionError(f"sum(H_l*W_l) does not match the value length {num_value}")
 
     def forward(self, query: torch.Tensor, key: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
                 identity: Optional[torch.Tensor] = None, query_pos: Optional[torch.Tensor] = None,
@@ -113,7 +119,7 @@ class MultiScaleDeformableAttention(nn.Module):
 
         bs, num_query, _ = query.shape
         _, num_value, _ = value.shape
-        self._check_shapes_once(spatial_shapes, num_value)
+        self._check_shapes(spatial_shapes, num_value, kwargs.get("level_shapes"))
         H, L, P = self.num_heads, self.num_levels, self.num_points
 
         value = self.value_proj(value)

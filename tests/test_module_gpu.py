@@ -9,11 +9,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def reference_module_forward(m, query, value, identity, query_pos, key_padding_mask, reference_points, spatial_shapes):
-    """py:270-363 re-assembled on the CPU in float64 around the oracle's core."""
+def reference_module_forward(m, query, value, identity, query_pos, key_padding_mask, reference_points, spatial_shapes,
+                             params=None):
+    """py:270-363 re-assembled on the CPU in float64 around the oracle's core (differentiable torch ops:
+    pass float64 leaf tensors as `params` / `query` / `value` to get the reference gradients by autograd)."""
     from oracle import msda_torch
     d = torch.float64
-    sd = {k: v.detach().cpu().to(d) for k, v in m.state_dict().items()}
+    sd = params if params is not None else {k: v.detach().cpu().to(d) for k, v in m.state_dict().items()}
     lin = lambda x, n: x @ sd[n + ".weight"].T + sd[n + ".bias"]
     query, value, identity = query.cpu().to(d), value.cpu().to(d), identity.cpu().to(d)
     if query_pos is not None:
@@ -80,6 +82,24 @@ def test_module_forward_backward_matches_reference_assembly(ref_dim, batch_first
     for p in m.parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all()
     assert m.sampling_offsets.weight.grad.abs().sum() > 0 and m.value_proj.weight.grad.abs().sum() > 0
+    # backward: input and parameter gradients against autograd through the float64 reference assembly
+    params = {k: v.detach().cpu().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    q64 = q.detach().cpu().double().requires_grad_(True)
+    v64 = q64 if ref_dim == 2 else val.detach().cpu().double().requires_grad_(True)
+    want2 = reference_module_forward(m, q64, v64, q64, pos, mask, ref_pts, shapes, params=params)
+    want2.square().mean().backward()
+
+    def gclose(got, ref, what):
+        # float32 GEMMs + float32 kernels against float64 autograd.  The offset branch is looser: a sample that the
+        # float32 location arithmetic puts on the other side of a bilinear cell boundary changes ITS grad_loc by O(1)
+        got, ref = got.detach().cpu().double(), ref.double()
+        err = (got - ref).abs().max().item()
+        tol = 2e-3 if "sampling_offsets" in what else 2e-4
+        assert err <= tol * ref.abs().max().item() + 1e-9, (what, err, ref.abs().max().item())
+
+    gclose(q.grad, q64.grad, "grad query")
+    for k, p in m.named_parameters():
+        gclose(p.grad, params[k].grad, "grad " + k)
 
 
 def test_module_autocast_bf16_and_fp16():
@@ -271,25 +291,45 @@ def test_fused_function_random_shapes_against_composition(seed):
         assert (a - b).abs().max() <= t * b.abs().max() + 1e-6, (name, what, float((a - b).abs().max()), float(b.abs().max()))
 
 
-def test_fused_function_refuses_deterministic_mode():
-    """No silent downgrade: the fused kernels have no bit-reproducible backward, so asking for one raises; the
-    module falls back to the unfused composition (whose backward honours the flag) on its own."""
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("masked", [False, True])
+def test_fused_function_deterministic_backward(ref_dim, masked):
+    """Deterministic mode: the fused Function keeps its fused forward and runs a bit-reproducible backward (the
+    unfused deterministic kernels + the chain rule through softmax / affine): identical bits across runs on a
+    contended shape, and the same gradients as the regular fused backward up to float summation order."""
     from ir_ads_b200 import MultiScaleDeformableAttention, functional
     from ir_ads_b200.functional import MSDeformAttnFusedFunction
     from ir_ads_b200.workloads import level_tensors
 
+    torch.manual_seed(5)
     levels = [(6, 9), (3, 5)]
     shapes, lsi = level_tensors(levels, DEV)
     S = sum(h * w for h, w in levels)
-    value = torch.randn(1, S, 2, 32, device=DEV, requires_grad=True)
-    offsets = torch.randn(1, 7, 2, 2, 4, 2, device=DEV, requires_grad=True)
-    logits = torch.randn(1, 7, 2, 8, device=DEV, requires_grad=True)
-    ref = torch.rand(1, 7, 2, 2, device=DEV)
-    out = MSDeformAttnFusedFunction.apply(value, shapes, lsi, offsets, logits, ref)
+    B, Q, H, D, L, P = 2, 900, 2, 32, 2, 4
+    value = torch.randn(B, S, H, D, device=DEV)
+    offsets = torch.randn(B, Q, H, L, P, 2, device=DEV) * 2.0
+    logits = torch.randn(B, Q, H, L * P, device=DEV)
+    ref = torch.rand(B, Q, L, ref_dim, device=DEV)
+    if ref_dim == 4:
+        ref[..., 2:] = ref[..., 2:] * 0.4 + 0.05
+    mask = (torch.rand(B, S, device=DEV) < 0.3) if masked else None
+    go = torch.randn(B, Q, H * D, device=DEV)
+
+    def grads():
+        leaves = [t.clone().requires_grad_(True) for t in (value, offsets, logits)]
+        MSDeformAttnFusedFunction.apply(leaves[0], shapes, lsi, leaves[1], leaves[2], ref, mask).backward(go)
+        return [t.grad for t in leaves]
+
+    base = grads()
     functional.set_deterministic(True)
     try:
-        with pytest.raises(RuntimeError, match="deterministic"):
-            out.sum().backward()
+        runs = [grads() for _ in range(3)]
+        for r in runs[1:]:
+            assert all(torch.equal(a, b) for a, b in zip(runs[0], r))
+        for a, b, name in zip(runs[0], base, ("grad_value", "grad_offsets", "grad_logits")):
+            assert (a - b).abs().max() <= 1e-4 * b.abs().max() + 1e-6, name
+        if masked:
+            assert float(runs[0][0][mask].abs().max()) == 0.0
         m = MultiScaleDeformableAttention(embed_dim=64, num_heads=2, num_levels=2, num_points=4, dropout=0.0,
                                           batch_first=True).to(DEV)
         q = torch.randn(1, S, 64, device=DEV, requires_grad=True)
