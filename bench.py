@@ -25,6 +25,7 @@ gradients per step.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -58,6 +59,15 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="extra MSDA_FLAG_* bits (experiments)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's batch per GPU; strong: --total-batch images split over the GPUs")
+    ap.add_argument("--total-batch", type=int, default=0, help="strong scaling: images in the whole job")
+    ap.add_argument("--mode", default="op", choices=["op", "train"],
+                    help="op: the core operator (the metric); train: batch-sharded module-level training step "
+                         "(projections + fused op, fwd+bwd, grad all-reduce overlapped with backward, optimizer)")
+    ap.add_argument("--regions", type=int, default=3, help="timed regions of --steps steps each (median reported)")
+    ap.add_argument("--no-graph", action="store_true", help="train mode: do not try CUDA-graph capture")
+    ap.add_argument("--amp", action="store_true", help="train mode: bf16 autocast (AMP config)")
     return ap.parse_args()
 
 
@@ -68,9 +78,12 @@ def config_dict(wl, args, extra=None):
         "levels": [list(x) for x in wl.levels], "batch_per_gpu": wl.batch, "num_query": wl.queries,
         "heads": wl.num_heads, "head_dim": wl.head_dim, "points": wl.num_points, "value_dtype": wl.value_dtype,
         "points_per_step_per_gpu": wl.points * args.layers, "dist": args.dist,
-        "l2_hygiene": "inputs larger than L2: 6 distinct layer input sets (~1.3 GB each) cycled per step",
+        "l2_hygiene": f"{args.layers} distinct layer input sets cycled per step "
+                      f"({wl.algorithmic_bytes()[0] / 1e6:.0f} MB of inputs each"
+                      f"{', larger than the 126 MB L2' if wl.batch >= 4 else '; plus an L2 flush (256 MB write) between timed regions'})",
         "parallelism": f"image-batch sharding x{args.gpus}, no collective inside the op"
                        + ("; per step one NCCL mean all-reduce of the projection-weight grads (5.5 MB)" if args.gpus > 1 else ""),
+        "scaling_mode": args.scaling, "total_batch": wl.batch * args.gpus,
     }
     if extra:
         cfg.update(extra)
@@ -239,12 +252,37 @@ def ncu_traffic(workload: str, kernel: str):
         return None
 
 
+def onchip_block(wl, fwd_ms, bwd_ms):
+    """The measured on-chip ceilings (profiles/microbench_ceilings.json) scaled to this workload's corner rows: the
+    kernels gather 4 corner rows of D channels per point through L1 and scatter as many through L2 reds; those rates,
+    not HBM, bound them.  Reported beside the HBM fraction, never instead of it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "microbench_ceilings.json")) as f:
+            c = json.load(f)
+    except Exception:
+        return None
+    if wl.value_dtype != "f32" or wl.head_dim != 32:
+        return None                                  # the ceilings were measured on 128-byte float rows
+    rows = wl.points * 4
+    k = rows / c["rows_measured"]
+    g1, g2, red = c["gather_l1_resident_ms"] * k, c["gather_l2_sourced_ms"] * k, c["red_v4_f32_l2_resident_ms"] * k
+    return {"corner_rows_per_launch": rows, "row_bytes": c["row_bytes"],
+            "ceilings_ms": {"fwd_gather_l1_resident": g1, "fwd_gather_l2_sourced": g2, "bwd_red_l2_rate": red},
+            "fwd_frac_of_onchip_ceiling": g2 / fwd_ms, "bwd_frac_of_onchip_ceiling": red / bwd_ms,
+            "ncu_counters_cfg2": c.get("ncu_counters_cfg2"),
+            "note": "ceiling / measured launch time; > 1 is possible for the backward because ~14 % of the corners of "
+                    "model-like inputs carry weight 0 (padding) and issue no red",
+            "source": "profiles/microbench_ceilings.json (tools/microbench/*.cu on this pool's B200s)"}
+
+
 def main():
     args = parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, wl)
         return
+
+    import dataclasses
 
     import ir_ads_b200
     from ir_ads_b200 import _lib, functional
@@ -261,6 +299,18 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    args.gpus = world
+    if args.scaling == "strong":
+        from ir_ads_b200.sharding import shard_batch
+        total = args.total_batch or wl.batch
+        _, per = shard_batch(total, world, rank)          # raises unless the batch divides evenly
+        wl = dataclasses.replace(wl, batch=per)
+    if args.mode == "train":
+        run_train_mode(args, wl, dev, rank, world, dist_on)
+        if dist_on:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     L = args.layers
     n_pts_layer = wl.points
@@ -275,7 +325,11 @@ def main():
         go = torch.randn(wl.batch, wl.queries, wl.num_heads * wl.head_dim, device=dev,
                          generator=torch.Generator(device=dev).manual_seed(7 + i)).to(out_dt)
         layers.append((value, shapes, lsi, loc, w, go))
-    # the training config's exchange step: mean all-reduce of the L modules' projection-weight grads
+    # small per-GPU batches (strong scaling) fit in L2: flush it between timed regions
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if wl.batch < 4 else None
+    # the training config's exchange step: mean all-reduce of the L modules' projection-weight grads.  In this (core
+    # operator) mode no projection runs, so the payload is the right size but synthetic; --mode train exchanges the
+    # gradients a real module backward produced, overlapped with it.
     bucket = None
     if dist_on:
         from ir_ads_b200 import MultiScaleDeformableAttention, sharding
@@ -315,29 +369,37 @@ def main():
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        launches0 = _lib.launch_count()
-        t_begin, t_end = ev(), ev()
-        t_begin.record()
-        for _ in range(args.steps):
-            step()
-        t_end.record()
-        barrier()
-        launches = _lib.launch_count() - launches0
+        # `regions` timed regions of exactly `steps` steps each, every one bracketed by barrier + synchronize;
+        # the median region is the reported one (one un-repeated sample gave an unexplained 0.90 outlier in r01)
+        region_ms = []
+        launches = 0
+        for _ in range(max(1, args.regions)):
+            if flush is not None:
+                flush.zero_()
+            barrier()
+            launches0 = _lib.launch_count()
+            t_begin, t_end = ev(), ev()
+            t_begin.record()
+            for _ in range(args.steps):
+                step()
+            t_end.record()
+            barrier()
+            launches = _lib.launch_count() - launches0
+            region_ms.append(t_begin.elapsed_time(t_end) / args.steps)
         clocks = sampler.stop()
-        ms_total = t_begin.elapsed_time(t_end)
 
         # per-kernel durations (same stream, separate short pass so event records do not perturb `value`)
         recs = []
         for _ in range(3):
             step(recs)
         torch.cuda.synchronize()
-        fwd_ms = statistics.mean(a.elapsed_time(b) for a, b, _ in recs)
-        bwd_ms = statistics.mean(b.elapsed_time(c) for _, b, c in recs)
+        fwd_ms = statistics.median(a.elapsed_time(b) for a, b, _ in recs)
+        bwd_ms = statistics.median(b.elapsed_time(c) for _, b, c in recs)
 
-    ms_step = ms_total / args.steps
     if dist_on:
         from ir_ads_b200.sharding import max_over_ranks
-        ms_step = max_over_ranks(ms_step, dev)
+        region_ms = [max_over_ranks(x, dev) for x in region_ms]
+    ms_step = statistics.median(region_ms)
     value_pts = n_pts_layer * L * world / (ms_step * 1e-3)
 
     # ---------------- e2e: public autograd API, host buffers ----------------
@@ -353,23 +415,32 @@ def main():
     if rank == 0:
         peak, peak_src = peak_hbm()
         achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+        flags_eff = args.flags | (_lib.FLAG_DETERMINISTIC if wl.deterministic else 0)
         bwd_name = _lib.lib().msda_dispatch_name(
             wl.head_dim, wl.num_levels, wl.num_points, wl.spatial_size, wl.num_heads,
-            _lib.MSDA_BF16 if wl.value_dtype == "bf16" else _lib.MSDA_F32, args.flags, 1).decode()
-        line = {
-            "metric": METRIC, "value": value_pts, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if wl.value_dtype == "f32" else "bf16(value) + f32 accumulate",
-            "data": "synthetic", "config": config_dict(wl, args),
-            "roofline": {"bound": "hbm", "kernel": bwd_name,
+            _lib.MSDA_BF16 if wl.value_dtype == "bf16" else _lib.MSDA_F32, flags_eff, 1).decode()
+        if wl.deterministic:
+            bwd_name += " (MSDA_FLAG_DETERMINISTIC: sorted segment reduction, several launches)"
+        roof = {"bound": "hbm", "kernel": bwd_name,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
-                "traffic": ncu_traffic(wl.name, bwd_name) if args.flags == 0 else None,
+                "traffic": ncu_traffic(wl.name, bwd_name) if args.flags == 0 and wl.batch == WORKLOADS[wl.name].batch else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes,
                 "launch_ms": bwd_ms, "note": "launch_ms includes the grad_value zero-fill memset issued by msda_backward",
                 "fwd": {"algorithmic_bytes_per_launch": fwd_bytes, "launch_ms": fwd_ms,
                         "achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "frac": fwd_bytes / (fwd_ms * 1e-3) / 1e9 / peak},
-                "fwd_bwd_frac": (fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak},
+                "fwd_bwd_frac": (fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak}
+        oc = onchip_block(wl, fwd_ms, bwd_ms) if not wl.deterministic else None
+        if oc is not None:
+            roof["onchip"] = oc
+        line = {
+            "metric": METRIC, "value": value_pts, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f32" if wl.value_dtype == "f32" else "bf16(value) + f32 accumulate",
+            "data": "synthetic", "config": config_dict(wl, args),
+            "timed_regions": {"count": len(region_ms), "ms_per_step": [round(x, 4) for x in region_ms],
+                              "reported": "median", "spread_pct": round(100.0 * (max(region_ms) - min(region_ms)) / ms_step, 2)},
+            "roofline": roof,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if e2e is not None:
@@ -377,11 +448,138 @@ def main():
         if ref_cuda is not None:
             line["reference_cuda_same_gpu"] = ref_cuda
         if not args.no_cpu_baseline and world >= 1:
-            line["cpu_baseline"] = cpu_baseline(wl, args.dist)
+            line["cpu_baseline"] = cpu_baseline(WORKLOADS[args.workload], args.dist)
         print(json.dumps(line), flush=True)
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# --mode train: BASELINE config 4, the batch-sharded deformable-DETR training step
+# --------------------------------------------------------------------------------------------
+def run_train_mode(args, wl, dev, rank, world, dist_on):
+    """One step = `layers` MultiScaleDeformableAttention MODULES chained (value/offset/weight/output projections through
+    cuBLAS, softmax + location affine + core op fused in the sm_100a kernels), forward + backward, the DDP-style mean
+    all-reduce of the projection-weight gradients launched per module from gradient hooks so that it overlaps the rest of
+    the backward (detectron2/detectron2/engine/defaults.py:60-79 wraps the model in DistributedDataParallel, whose
+    buckets do the same), and a fused AdamW step.  Images are sharded over the ranks (total batch fixed under --scaling
+    strong); no collective inside the op.  The step is replayed from one CUDA graph when capture succeeds."""
+    import torch.distributed as dist
+    from ir_ads_b200 import MultiScaleDeformableAttention, _lib, sharding
+    from ir_ads_b200.workloads import _pixel_centres, level_tensors
+
+    L = args.layers
+    E = wl.num_heads * wl.head_dim
+    torch.manual_seed(0)                                    # identical initial weights on every rank (DDP broadcast)
+    mods = torch.nn.ModuleList([MultiScaleDeformableAttention(E, wl.num_heads, wl.num_levels, wl.num_points, dropout=0.0,
+                                                              batch_first=True) for _ in range(L)]).to(dev)
+    for m in mods:
+        with torch.no_grad():                               # data-dependent offsets / weights, as after some training
+            m.sampling_offsets.weight.normal_(0, 0.02)
+            m.attention_weights.weight.normal_(0, 0.1)
+    params = sharding.projection_parameters(mods)
+    sync = sharding.OverlappedGradSync([sharding.projection_parameters([m]) for m in mods])
+    opt = torch.optim.AdamW(params, lr=1e-5, fused=True, capturable=True)
+    shapes, lsi = level_tensors(wl.levels, dev)
+    level_shapes = list(wl.levels)
+    S = wl.spatial_size
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    x = torch.randn(wl.batch, S, E, device=dev, generator=g)
+    pos = torch.randn(wl.batch, S, E, device=dev, generator=g) * 0.1
+    ref = _pixel_centres(wl.levels, dev)[None, :, None, :].expand(wl.batch, S, wl.num_levels, 2).contiguous()
+    amp = torch.autocast("cuda", dtype=torch.bfloat16) if args.amp else contextlib.nullcontext()
+
+    def fwd_bwd():
+        sync.zero_()
+        with amp:
+            h = x
+            for m in mods:
+                h = m(h, query_pos=pos, reference_points=ref, spatial_shapes=shapes, level_start_index=lsi,
+                      level_shapes=level_shapes)
+            loss = h.float().square().mean()
+        loss.backward()                                     # hooks launch the per-module all-reduces as grads land
+        sync.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        fwd_bwd()
+    barrier()
+    graph, how = None, "eager"
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fwd_bwd()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = fwd_bwd()
+            graph.replay()
+            torch.cuda.synchronize()
+            how = "one CUDA graph per step (forward, backward, all-reduces, AdamW)"
+        except Exception as exc:                            # capture of NCCL work is not guaranteed everywhere
+            graph = None
+            how = f"eager (graph capture failed: {type(exc).__name__})"
+            torch.cuda.synchronize()
+    step = graph.replay if graph is not None else fwd_bwd
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    region_ms = []
+    launches = 0
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(max(1, args.regions)):
+        flush.zero_()
+        barrier()
+        l0 = _lib.launch_count()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(args.steps):
+            step()
+        t1.record()
+        barrier()
+        launches = _lib.launch_count() - l0
+        region_ms.append(t0.elapsed_time(t1) / args.steps)
+    clocks = sampler.stop()
+    if dist_on:
+        region_ms = [sharding.max_over_ranks(v, dev) for v in region_ms]
+    ms = statistics.median(region_ms)
+    pts = wl.points * L * world
+    if rank == 0:
+        kernels_per_step = 2 * L                            # fused forward + fused backward per module
+        line = {
+            "metric": "msda_training_step_sampled_points_per_s", "value": pts / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "bf16 autocast (bf16 value, f32 accumulate)" if args.amp else "f32", "data": "synthetic",
+            "config": {"workload": f"{wl.name}: batch-sharded deformable-DETR training step -- {L} MSDeformAttn modules "
+                                   "(projections + fused core op) fwd+bwd, per-module NCCL mean all-reduce of the "
+                                   "projection-weight grads from gradient hooks, fused AdamW",
+                       "levels": [list(v) for v in wl.levels], "batch_per_gpu": wl.batch, "total_batch": wl.batch * world,
+                       "num_query": wl.queries, "heads": wl.num_heads, "head_dim": wl.head_dim, "points": wl.num_points,
+                       "params_exchanged": sum(p.numel() for p in params), "execution": how,
+                       "l2_hygiene": "256 MB L2 flush between timed regions",
+                       "parallelism": f"image-batch sharding x{world}, no collective inside the op; "
+                                      f"{L} all-reduces of 0.92 MB per step overlapped with backward"},
+            "timed_regions": {"count": len(region_ms), "ms_per_step": [round(v, 4) for v in region_ms],
+                              "reported": "median", "spread_pct": round(100.0 * (max(region_ms) - min(region_ms)) / ms, 2)},
+            "gpu_launches": int(launches) if graph is None else kernels_per_step * args.steps,
+            "gpu_launches_note": "graph replays launch the captured kernels without passing the library's counter"
+                                 if graph is not None else "counted by the library",
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
 
 
 def run_e2e(wl, layers, dev, dist_on, world, args):

@@ -90,10 +90,12 @@ extern "C" {
  * levels on a side stream, head-major strips) that were measured slower and removed; they are reserved and
  * ignored. */
 
-/* Backward, encoder form (Q == S, query i is pixel i of the pyramid), D in {32, 64}, float accumulation:
+/* EXPERIMENT BUILDS ONLY (msda_build_config() & MSDA_BUILD_EXPERIMENTS; the product library ignores both bits).
+ * Backward, encoder form (Q == S, query i is pixel i of the pyramid), D in {32, 64}, float accumulation:
  * grad_value contributions of an 8x8 query tile of one head are pre-added ON THE SM (pixel-keyed lists in
  * shared memory, csrc/msda_fold.cuh) and leave it as ONE vector red per distinct destination row instead of one
- * per (point, corner): ~5x fewer reds on model-like inputs (profiles/r02a_fold_rate_cfg2.json).
+ * per (point, corner): 5.5x fewer reds on model-like inputs (profiles/r02a_fold_rate_cfg2.json) -- and 2-2.5x
+ * SLOWER, because the bookkeeping more than doubles the instruction count (profiles/r02b_fold_experiment.txt).
  * grad_sampling_loc / grad_attn_weight are bit-identical to the other kernels'; grad_value differs by float
  * summation order only.  FOLD_OFF wins over FOLD_ON; an explicit ORDER_* flag, MSDA_FLAG_DETERMINISTIC and
  * MSDA_FLAG_FORCE_GENERIC also select the non-folding kernels. */
@@ -108,6 +110,10 @@ extern "C" {
 #define MSDA_FLAG_NO_GRAD_VALUE (1u << 11)
 
 int msda_abi_version(void);
+/* How this library was built: 0 for the product library. */
+#define MSDA_BUILD_EXPERIMENTS 1u /* -DMSDA_EXPERIMENTS: the measured-slower experiments are compiled in   */
+#define MSDA_BUILD_SLIM 2u        /* -DMSDA_EXP_SLIM: only D = 32, P in {4, 8} of the plain operator       */
+unsigned msda_build_config(void);
 
 /* Forward.  Returns MSDA_OK or an error code.  B*Q*H*D == 0 is a no-op. */
 int msda_forward(void* stream, const void* value, const int64_t* spatial_shapes,

@@ -53,6 +53,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     vp, i, u, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t
     lib.msda_abi_version.restype = i
     lib.msda_abi_version.argtypes = []
+    lib.msda_build_config.restype = u
+    lib.msda_build_config.argtypes = []
     lib.msda_forward.restype = i
     lib.msda_forward.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, i, u]
     lib.msda_backward_workspace_bytes.restype = sz
@@ -102,6 +104,11 @@ def check(status: int, what: str) -> None:
         name = handle.msda_status_string(status).decode()
         detail = handle.msda_last_error_message().decode()
         raise MSDAError(f"{what}: {name}: {detail}")
+
+
+def has_experiments() -> bool:
+    """True for a -DMSDA_EXPERIMENTS build (tools/build_variant.sh); the product library has none."""
+    return bool(lib().msda_build_config() & 1)
 
 
 def launch_count() -> int:

@@ -36,7 +36,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   return fail(MSDA_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
-void count_launch() { count_launch(); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 bool fast_ok(const Dims& d, int dtype, unsigned flags) {
   if (flags & MSDA_FLAG_FORCE_GENERIC) return false;
@@ -239,6 +239,17 @@ size_t elem_size(int dtype) { return dtype == MSDA_F64 ? 8 : (dtype == MSDA_BF16
 extern "C" {
 
 int msda_abi_version(void) { return MSDA_ABI_VERSION; }
+
+unsigned msda_build_config(void) {
+  unsigned c = 0;
+#ifdef MSDA_EXPERIMENTS
+  c |= MSDA_BUILD_EXPERIMENTS;
+#endif
+#ifdef MSDA_EXP_SLIM
+  c |= MSDA_BUILD_SLIM;
+#endif
+  return c;
+}
 
 uint64_t msda_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

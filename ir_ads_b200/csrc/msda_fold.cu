@@ -1,6 +1,21 @@
 // msda_fold.cu -- instantiations and dispatch of the folding encoder backward (msda_fold.cuh).
-#include "msda_fold.cuh"
+//
+// EXPERIMENT, compiled only with -DMSDA_EXPERIMENTS (tools/build_variant.sh); the product library carries stubs.
+// Measured on B200 at cfg 2 (profiles/r02b_fold_experiment.txt): the fold removes 82 % of the reds (57 M red sectors
+// instead of 312 M, crossbar port 9 % busy instead of 93 %) but its bookkeeping costs 2.0 G warp instructions
+// against 0.9 G, and the backward takes 3.1 - 4.2 ms instead of 1.67 ms.
 #include "msda_fast_launch.cuh"
+
+#ifndef MSDA_EXPERIMENTS
+namespace msda_host {
+bool fold_applies(const Dims&, int, unsigned) { return false; }
+int bwd_fold(cudaStream_t, const Dims&, int, const void*, const void*, const int64_t*, const int64_t*, const void*,
+             const void*, float*, void*, void*, const msda::FusedArgs*) {
+  return fail(MSDA_ERR_UNSUPPORTED, "the folding backward is compiled into experiment builds only");
+}
+}  // namespace msda_host
+#else
+#include "msda_fold.cuh"
 
 namespace msda_host {
 
@@ -68,10 +83,7 @@ bool fold_applies(const Dims& d, int dtype, unsigned flags) {
   if (d.Q != d.S) return false;                       // query i must be pixel i of the pyramid
   if (!(d.D == 32 || d.D == 64)) return false;
   if (fold_tile(d) == 0) return false;
-#if !MSDA_FOLD_DEFAULT
-  if (!(flags & MSDA_FLAG_FOLD_ON)) return false;
-#endif
-  return true;
+  return (flags & MSDA_FLAG_FOLD_ON) != 0;
 }
 
 int bwd_fold(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
@@ -94,3 +106,4 @@ int bwd_fold(cudaStream_t st, const Dims& d, int dtype, const void* go, const vo
 }
 
 }  // namespace msda_host
+#endif  // MSDA_EXPERIMENTS

@@ -67,6 +67,68 @@ class GradBucket:
             self.flat.div_(dist.get_world_size(group))
 
 
+class OverlappedGradSync:
+    """DDP-style bucketed gradient exchange for the MSDeformAttn modules of a layer stack: one bucket per module
+    (8 projection tensors, 230 272 parameters = 0.92 MB), whose mean all-reduce is LAUNCHED FROM A GRADIENT HOOK the
+    moment the module's last gradient has been accumulated, so it runs (on NCCL's own stream) while autograd is still
+    working on the earlier modules -- what DistributedDataParallel's reducer does for the reference
+    (detectron2/detectron2/engine/defaults.py:60-79).  ``finish()`` waits for the outstanding collectives and scales
+    by 1 / world_size.  Gradients are views into one flat buffer (see GradBucket), so nothing is copied.
+
+    Without an initialised process group (or world_size 1) the hooks only count; ``finish()`` is then a no-op."""
+
+    def __init__(self, module_params: Sequence[Sequence[torch.nn.Parameter]], group=None):
+        self.group = group
+        self._pending: List[int] = []
+        self._works: list = []
+        self._handles = []
+        all_params = [p for ps in module_params for p in ps]
+        self.all = GradBucket(all_params)              # one flat buffer; per-module buckets are slices of it
+        o = 0
+        self.slices = []
+        for k, ps in enumerate(module_params):
+            n = sum(p.numel() for p in ps)
+            self.slices.append(self.all.flat[o:o + n])
+            o += n
+            self._pending.append(len(ps))
+            for p in ps:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(k)))
+        self._sizes = [len(ps) for ps in module_params]
+
+    def _active(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _make_hook(self, k: int):
+        def hook(_param):
+            self._pending[k] -= 1
+            if self._pending[k] == 0 and self._active():
+                self._works.append(dist.all_reduce(self.slices[k], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        return hook
+
+    def zero_(self) -> None:
+        """Start of a step: clear the gradients (the views stay attached) and re-arm the hooks."""
+        self.all.zero_()
+        self._pending = list(self._sizes)
+        self._works = []
+
+    def finish(self) -> None:
+        """End of backward: wait for the collectives launched by the hooks, then grad <- mean over ranks."""
+        for w in self._works:
+            w.wait()
+        if self._active():
+            launched = len(self._works)
+            if launched != len(self.slices):             # a module whose parameters got no gradient this step
+                raise RuntimeError(f"{len(self.slices) - launched} bucket(s) never became ready: every projection "
+                                   "weight must receive a gradient (find_unused_parameters=False semantics)")
+            self.all.flat.div_(dist.get_world_size(self.group))
+        self._works = []
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def max_over_ranks(value: float, device) -> float:
     """Step time of the job = the slowest rank's (timing rule of bench.py)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

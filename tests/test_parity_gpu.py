@@ -43,6 +43,12 @@ def run_cuda(value, shapes, lsi, loc, w, go, dtype=torch.float32, flags=0):
     return f(out), f(v.grad), f(lo.grad), f(ww.grad)
 
 
+def needs_experiments():
+    """The folding backward lives in -DMSDA_EXPERIMENTS builds only (MSDA_B200_LIB=build/variants/lib_exp.so)."""
+    if not _mods()[1].has_experiments():
+        pytest.skip("product library: experiment kernels not compiled in (tools/build_variant.sh exp -DMSDA_EXPERIMENTS)")
+
+
 def nerr(a, b):
     """max |a-b| normalised by max |b|."""
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
@@ -162,6 +168,7 @@ def test_row_orders_agree(D, P, dtype):
     value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 0, 4, D, P, "encoder", "model", 3, value_dtype=dtype)
     go = torch.randn(2, value.shape[1], 4 * D, generator=torch.Generator().manual_seed(1)).to(dtype)
     linear = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=_lib.FLAG_ORDER_LINEAR)
+    # (FOLD_ON selects the folding backward in experiment builds and is ignored by the product library)
     for flag in (_lib.FLAG_ORDER_STRIP, _lib.FLAG_ORDER_TILE2D, _lib.FLAG_FOLD_ON, _lib.FLAG_FOLD_OFF, 0):
         other = run_cuda(value, shapes, lsi, loc, w, go, dtype, flags=flag)
         assert np.array_equal(other[0], linear[0]) and np.array_equal(other[2], linear[2]) and np.array_equal(other[3], linear[3])
@@ -196,6 +203,7 @@ def test_folding_backward_against_oracle(D, L, P, dist, dtype):
     """grad_value pre-added on the SM == the one-red-per-corner path == the fp64 oracle; grad_loc / grad_w are
     untouched by the fold (bit-identical).  (32, 8, 4) takes the 8x8 tile with a runtime point count, (32, 5, 8)
     the 8x4 tile; (32, 16, 4) has no folding instantiation that fits shared memory and must fall back cleanly."""
+    needs_experiments()
     _, _lib, _, workloads, msda_c, _ = _mods()
     levels = [(19, 27), (10, 14), (5, 7), (3, 4), (2, 2), (1, 1), (1, 2), (2, 1), (1, 1), (1, 1), (1, 1), (1, 1), (1, 1),
               (1, 1), (1, 1), (1, 1)][:L]
@@ -214,6 +222,7 @@ def test_folding_backward_against_oracle(D, L, P, dist, dtype):
 def test_folding_backward_table_overflow():
     """Uniformly random locations on two large levels: an 8 x 8 query tile touches ~3800 distinct pixels, more than
     the 2048-slot table holds, so part of the contributions take the direct-red fallback of the filing lane."""
+    needs_experiments()
     _, _lib, _, workloads, msda_c, _ = _mods()
     levels = [(64, 64), (48, 48)]
     value, shapes, lsi, loc, w = workloads.make_inputs(levels, 1, 0, 2, 32, 8, "encoder", "test", 5)
@@ -230,6 +239,7 @@ def test_folding_backward_table_overflow():
 def test_folding_backward_dispatch():
     """The fold is one kernel launch; it applies to the encoder form only (Q == S) and never under an explicit row
     order, the deterministic flag or the generic flag."""
+    needs_experiments()
     ir, _lib, functional, workloads, _, _ = _mods()
     h = _lib.lib()
     value, shapes, lsi, loc, w = workloads.make_inputs([(21, 37), (11, 19)], 1, 0, 4, 32, 4, "encoder", "model", 2, DEV)

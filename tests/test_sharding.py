@@ -70,6 +70,62 @@ def test_grad_bucket_allreduce_world2_gloo():
     assert (res[0][2], res[0][3], res[1][2], res[1][3]) == (0, 4, 4, 4)
 
 
+def _hook_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                      # identical weights on every rank
+    lins = [torch.nn.Linear(6, 6) for _ in range(3)]       # three "modules" chained, one bucket each
+    sync = sharding.OverlappedGradSync([[l.weight, l.bias] for l in lins])
+    ok = True
+    for step in range(2):                     # two steps: the hooks re-arm
+        sync.zero_()
+        x = torch.full((4, 6), float(rank + 1 + step))
+        h = x
+        for l in lins:
+            h = l(h)
+        h.sum().backward()                    # hooks fire last module first, launching its all-reduce
+        launched = len(sync._works)
+        sync.finish()
+        # reference: the same computation for every rank's input, averaged
+        want = [torch.zeros_like(p) for l in lins for p in (l.weight, l.bias)]
+        for r in range(world):
+            ps = [p.detach().clone().requires_grad_(True) for l in lins for p in (l.weight, l.bias)]
+            h = torch.full((4, 6), float(r + 1 + step))
+            for i in range(3):
+                h = h @ ps[2 * i].T + ps[2 * i + 1]
+            h.sum().backward()
+            for wv, p in zip(want, ps):
+                wv += p.grad / world
+        got = [p.grad for l in lins for p in (l.weight, l.bias)]
+        ok = ok and launched == 3 and all(torch.allclose(a, b, rtol=1e-5, atol=1e-6) for a, b in zip(got, want))
+        ok = ok and all(p.grad.untyped_storage().data_ptr() == sync.all.flat.untyped_storage().data_ptr()
+                        for l in lins for p in (l.weight, l.bias))
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_overlapped_grad_sync_hooks_world2_gloo():
+    """The training config's exchange (bench.py --mode train): per-module buckets all-reduced from gradient hooks
+    while backward is still running give the mean gradient over ranks, step after step."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_hook_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    assert res[0] and res[1]
+
+
+def test_overlapped_grad_sync_without_process_group():
+    lin = torch.nn.Linear(3, 3)
+    sync = sharding.OverlappedGradSync([[lin.weight, lin.bias]])
+    sync.zero_()
+    lin(torch.ones(2, 3)).sum().backward()
+    sync.finish()
+    assert torch.allclose(lin.bias.grad, torch.full((3,), 2.0))
+    sync.remove()
+
+
 def test_bucket_without_process_group_is_identity():
     from ir_ads_b200 import MultiScaleDeformableAttention
 
