@@ -202,6 +202,27 @@ int msda_dcnv3_backward(void* stream, const void* grad_output, const void* input
                         unsigned flags);
 
 /*
+ * Fused residual add + LayerNorm: the epilogue that follows every MSDeformAttn call and every
+ * FFN in the reference's transformer layers -- x = x + identity; x = norm(x)
+ * (/root/reference/detrex/layers/transformer.py:152-192; the residuals are added at multi_scale_deform_attn.py:363 and
+ * detrex/layers/mlp.py:127-132) -- as one pass instead of an add kernel plus a LayerNorm kernel.
+ *   a, b, y, grad_y, grad_x   [rows, channels]  dtype (MSDA_F32 or MSDA_BF16), contiguous
+ *   gamma, beta, grad_gamma, grad_beta  [channels] float;   mean, rstd  [rows] float (saved by forward for backward)
+ * forward:  y = (a + b - mean) * rstd * gamma + beta, statistics over the channels, fp32 arithmetic.
+ * backward: grad_x = d loss / d (a + b) -- the gradient of BOTH addends -- plus grad_gamma / grad_beta, reduced in a
+ *           fixed order (bit-reproducible); a + b is recomputed, never stored.  Needs a workspace of
+ *           msda_add_layernorm_workspace_bytes(rows, channels).
+ * channels must be a multiple of 4 and at most 1024 (MSDA_ERR_UNSUPPORTED otherwise).
+ */
+size_t msda_add_layernorm_workspace_bytes(int64_t rows, int channels);
+int msda_add_layernorm_forward(void* stream, const void* a, const void* b, const float* gamma, const float* beta,
+                               int64_t rows, int channels, float eps, void* y, float* mean, float* rstd, int dtype);
+int msda_add_layernorm_backward(void* stream, const void* grad_y, const void* a, const void* b, const float* gamma,
+                                const float* mean, const float* rstd, int64_t rows, int channels, void* grad_x,
+                                float* grad_gamma, float* grad_beta, void* workspace, size_t workspace_bytes,
+                                int dtype);
+
+/*
  * Test hook: the integer bookkeeping the float kernels derive from every sampling point.
  *   corner_offsets [B*Q*H*L*P, 4] int64  flat element offset (channel 0) of the four bilinear
  *                  corners inside `value`, -1 for a zero-padded corner or a gated-out point;

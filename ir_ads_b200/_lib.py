@@ -68,6 +68,13 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_fused_backward.restype = i
     lib.msda_fused_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, vp, i, i, i, i, i, i, i, vp, vp, vp, vp,
                                         sz, i, u]
+    i64, f32 = ctypes.c_int64, ctypes.c_float
+    lib.msda_add_layernorm_workspace_bytes.restype = sz
+    lib.msda_add_layernorm_workspace_bytes.argtypes = [i64, i]
+    lib.msda_add_layernorm_forward.restype = i
+    lib.msda_add_layernorm_forward.argtypes = [vp, vp, vp, vp, vp, i64, i, f32, vp, vp, vp, i]
+    lib.msda_add_layernorm_backward.restype = i
+    lib.msda_add_layernorm_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i, vp, vp, vp, vp, sz, i]
     lib.msda_debug_bookkeeping.restype = i
     lib.msda_debug_bookkeeping.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]
     lib.msda_status_string.restype = ctypes.c_char_p

@@ -27,10 +27,11 @@ compile msda_fwd & pids+=($!)
 compile msda_bwd & pids+=($!)
 compile msda_bwd_aux & pids+=($!)
 compile msda_fold "${here}/msda_fold.cuh" & pids+=($!)
+compile msda_epilogue & pids+=($!)
 rc=0
 for p in "${pids[@]}"; do wait "${p}" || rc=1; done
 [[ ${rc} == 0 ]] || { echo "build failed"; exit 1; }
 "${NVCC}" -gencode arch=compute_100a,code=sm_100a -shared -o "${out}" "${obj}"/msda_capi.o "${obj}"/msda_fwd.o \
-  "${obj}"/msda_bwd.o "${obj}"/msda_bwd_aux.o "${obj}"/msda_fold.o
+  "${obj}"/msda_bwd.o "${obj}"/msda_bwd_aux.o "${obj}"/msda_fold.o "${obj}"/msda_epilogue.o
 cat "${obj}"/build_msda_*.log > "${obj}/build.log" 2>/dev/null || true
 echo "built ${out}"

@@ -20,6 +20,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
+from .epilogue import add_layer_norm, add_layer_norm_supported
 from .module import MultiScaleDeformableAttention
 
 
@@ -91,7 +92,10 @@ class FFN(nn.Module):
 
 
 class DeformableEncoderLayer(nn.Module):
-    """self_attn (MSDeformAttn) -> norm -> ffn -> norm, post-norm, batch-first."""
+    """self_attn (MSDeformAttn) -> norm -> ffn -> norm, post-norm, batch-first
+    (BaseTransformerLayer with operation_order ("self_attn", "norm", "ffn", "norm"), detrex/layers/transformer.py:152-192).
+    Both ``x + identity; norm(x)`` epilogues run as ONE fused kernel each (ir_ads_b200/epilogue.py) where it applies
+    (CUDA, float32 / bfloat16); ``fuse_epilogue = False`` restores the op-by-op composition."""
 
     def __init__(self, embed_dim=256, num_heads=8, feedforward_dim=1024, attn_dropout=0.1, ffn_dropout=0.1,
                  num_feature_levels=4, num_points=4):
@@ -103,10 +107,18 @@ class DeformableEncoderLayer(nn.Module):
             dropout=attn_dropout, batch_first=True)])
         self.ffns = nn.ModuleList([FFN(embed_dim, feedforward_dim, ffn_dropout)])
         self.norms = nn.ModuleList([nn.LayerNorm(embed_dim), nn.LayerNorm(embed_dim)])
+        self.fuse_epilogue = True
 
     def forward(self, query, query_pos=None, query_key_padding_mask=None, reference_points=None,
                 spatial_shapes=None, level_start_index=None, **kwargs):
         # self_attn: key = value = query, key_padding_mask = query_key_padding_mask (transformer.py:152-167)
+        if self.fuse_epilogue and add_layer_norm_supported(query):
+            attn = self.attentions[0](query, None, None, None, query_pos=query_pos,
+                                      key_padding_mask=query_key_padding_mask, reference_points=reference_points,
+                                      spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                                      level_shapes=kwargs.get("level_shapes"), add_identity=False)
+            query = add_layer_norm(attn, query, self.norms[0])                    # norm(attn + identity)
+            return add_layer_norm(self.ffns[0].layers(query), query, self.norms[1])   # norm(ffn(x) + x)
         query = self.attentions[0](query, None, None, None, query_pos=query_pos,
                                    key_padding_mask=query_key_padding_mask, reference_points=reference_points,
                                    spatial_shapes=spatial_shapes, level_start_index=level_start_index,
@@ -166,6 +178,11 @@ class DeformableCrossAttentionBlock(nn.Module):
     def forward(self, query, memory, query_pos, reference_points, valid_ratios, spatial_shapes, level_start_index,
                 key_padding_mask=None):
         ref_in = decoder_reference_points_input(reference_points, valid_ratios)
+        if add_layer_norm_supported(query):
+            out = self.attn(query, None, memory, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
+                            reference_points=ref_in, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                            add_identity=False)
+            return add_layer_norm(out, query, self.norm)
         out = self.attn(query, None, memory, None, query_pos=query_pos, key_padding_mask=key_padding_mask,
                         reference_points=ref_in, spatial_shapes=spatial_shapes, level_start_index=level_start_index)
         return self.norm(out)

@@ -15,7 +15,9 @@ What differs from the reference module:
   * bfloat16 activations (autocast bf16) go to the bf16-value kernel with float32 sampling
     locations / weights instead of failing in the float-only dispatch; float16 is widened to
     float32 around the op exactly as the reference does (py:343, :355-356);
-  * there is no CPU branch (py:350-353): a CPU tensor raises.
+  * there is no CPU branch (py:350-353): a CPU tensor raises;
+  * ``add_identity=False`` (keyword, default True) returns ``dropout(output_proj(...))`` WITHOUT the residual
+    (py:363), for callers that fuse ``+ identity`` into the LayerNorm that follows (ir_ads_b200/epilogue.py).
 """
 from __future__ import annotations
 
@@ -161,6 +163,8 @@ class MultiScaleDeformableAttention(nn.Module):
             output = self.output_proj(output)
             if not self.batch_first:
                 output = output.permute(1, 0, 2)
+            if not kwargs.get("add_identity", True):      # the caller fuses the residual into its LayerNorm (epilogue.py)
+                return self.dropout(output)
             return self.dropout(output) + identity
 
         weights = logits.softmax(-1).view(bs, num_query, H, L, P)
@@ -185,4 +189,6 @@ class MultiScaleDeformableAttention(nn.Module):
         output = self.output_proj(output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)
+        if not kwargs.get("add_identity", True):
+            return self.dropout(output)
         return self.dropout(output) + identity
