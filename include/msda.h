@@ -78,6 +78,9 @@ extern "C" {
 /* With MSDA_FLAG_DETERMINISTIC: use the fixed-point RED path even where the sorted segment reduction
  * (msda_det.cuh) is available (A/B testing; both give the same bits). */
 #define MSDA_FLAG_DET_ATOMIC (1u << 6)
+/* With MSDA_FLAG_DETERMINISTIC (sorted path): fill the bins with a separate pass over the locations instead of from
+ * the backward kernel itself (A/B testing; both give the same bits, the separate pass is slower). */
+#define MSDA_FLAG_DET_SEPARATE_FILL (1u << 14)
 #define MSDA_FLAG_FORCE_GENERIC (1u << 1) /* bypass the D in {16,32,64,128} fast kernels             */
 /* Row order = which rows a CTA works on.  A scheduling choice only: results never depend on it.  Without an order
  * flag the library picks (forward: LINEAR; backward: the folding encoder kernel when it applies, else STRIP). */

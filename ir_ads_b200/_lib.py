@@ -27,6 +27,7 @@ FLAG_DET_ATOMIC = 1 << 6
 FLAG_NO_GRAD_VALUE = 1 << 11
 FLAG_FOLD_ON = 1 << 12
 FLAG_FOLD_OFF = 1 << 13
+FLAG_DET_SEPARATE_FILL = 1 << 14
 ABI_VERSION = 3
 
 _lock = threading.Lock()

@@ -30,6 +30,23 @@ int bwd_fast_noscatter(cudaStream_t st, const Dims& d, int dtype, const void* go
 #undef MSDA_DISPATCH_ORDER
 }
 
+// backward without the scatter that also files every in-range point under its bilinear cell (deterministic sorted
+// path: replaces det_bin_kernel<true> + the plain no-scatter backward), LINEAR order
+int bwd_fast_emit(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
+                  const int64_t* lsi, const void* loc, const void* w, void* gl, void* gw, int* cursor,
+                  const int* bin_start, void* entries) {
+  msda::EmitArgs ea{cursor, bin_start, static_cast<int4*>(entries)};
+#define MSDA_DISPATCH_ORDER MSDA_ORDER_LINEAR
+#define CALL_BWD(D_, VT_, PT_, ORD_)                                                                            \
+  launch_bwd_fast<D_, VT_, PT_, kBwdThreads, ORD_, msda::EmitEntries>(st, d, go, value, shapes, lsi, loc, w,   \
+                                                                      (msda::EmitEntries*)nullptr, gl, gw, nullptr, \
+                                                                      msda::FusedArgs{}, ea)
+  if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_BWD);
+  MSDA_DISPATCH_D(__nv_bfloat16, CALL_BWD);
+#undef CALL_BWD
+#undef MSDA_DISPATCH_ORDER
+}
+
 #ifdef MSDA_EXP_SLIM
 int bwd_fused(cudaStream_t, const Dims&, int, const void*, const void*, const int64_t*, const int64_t*, const void*,
               const void*, float*, void*, void*, msda::FusedArgs) {

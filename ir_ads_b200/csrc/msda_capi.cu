@@ -419,13 +419,23 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
       count();
       msda::det_scan_add_kernel<<<(unsigned)lay.scan_blocks, 256, 0, st>>>(bins, sums, lay.n_scan);
       count();
-      msda::det_bin_kernel<true><<<g_bin, 256, 0, st>>>(loc, w, spatial_shapes, level_start_index, d.H, d.L, d.Q, d.P,
-                                                        n_pts, cursor, bins, entries);
-      count();
       MSDA_CUDA(cudaGetLastError());
-      if (int s2 = bwd_fast_noscatter(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
-                                      attn_weight, grad_sampling_loc, grad_attn_weight))
+      // entries are filed by the backward kernel itself (ACC = EmitEntries): the lane that has just built a point's
+      // record takes the cursor atomic and writes the 16-byte entry, so the separate fill pass (det_bin_kernel<true>:
+      // re-read of every location / weight + the coordinate arithmetic a second time) is gone
+      if (flags & MSDA_FLAG_DET_SEPARATE_FILL) {
+        msda::det_bin_kernel<true><<<g_bin, 256, 0, st>>>(loc, w, spatial_shapes, level_start_index, d.H, d.L, d.Q, d.P,
+                                                          n_pts, cursor, bins, entries);
+        count();
+        MSDA_CUDA(cudaGetLastError());
+        if (int s2 = bwd_fast_noscatter(st, d, dtype, grad_output, value, spatial_shapes, level_start_index,
+                                        sampling_loc, attn_weight, grad_sampling_loc, grad_attn_weight))
+          return s2;
+      } else if (int s2 = bwd_fast_emit(st, d, dtype, grad_output, value, spatial_shapes, level_start_index,
+                                        sampling_loc, attn_weight, grad_sampling_loc, grad_attn_weight, cursor, bins,
+                                        entries)) {
         return s2;
+      }
       if (!det_dense(d)) {
         if (dtype == MSDA_F32)
           return det_gather<float>(st, d, grad_output, entries, bins, spatial_shapes, level_start_index, scale, grad_value);

@@ -143,7 +143,9 @@ struct LevelTab {
   int tiles_x[kFastMaxLevels];     // tile orders only
   int tile_begin[kFastMaxLevels];  // tile orders only: first tile index of the level
   int total_tiles;                 // tile orders only
-  int pad[3];
+  int cells_per_bh;                // EMIT only (deterministic sorted path): bins per (image, head), see msda_det.cuh
+  int cell_begin[kFastMaxLevels];  // EMIT only: first bin of the level inside one (image, head) block
+  int pad[2];
 };
 
 template <int TW, int TH>
@@ -167,12 +169,21 @@ __device__ __forceinline__ void load_levels(LevelTab* tab, const int64_t* shapes
   __syncthreads();
 }
 
-// LINEAR / STRIP orders need no tile table: one barrier, no serial section
+// LINEAR / STRIP orders need no tile table: one barrier, no serial section.  CELLS: also the bin table of the
+// deterministic sorted path (cells of the extended (H+1) x (W+1) grids, msda_det.cuh) -- thread l sums its own prefix.
+template <bool CELLS = false>
 __device__ __forceinline__ void load_levels_plain(LevelTab* tab, const int64_t* shapes, const int64_t* lsi, int L) {
   if (threadIdx.x < L) {
     tab->H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
     tab->W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
     tab->start[threadIdx.x] = (int)lsi[threadIdx.x];
+    if constexpr (CELLS) {
+      int acc = 0;
+      for (int k = 0; k < (int)threadIdx.x; ++k) acc += ((int)shapes[2 * k] + 1) * ((int)shapes[2 * k + 1] + 1);
+      tab->cell_begin[threadIdx.x] = acc;
+      if ((int)threadIdx.x == L - 1)
+        tab->cells_per_bh = acc + ((int)shapes[2 * threadIdx.x] + 1) * ((int)shapes[2 * threadIdx.x + 1] + 1);
+    }
   }
   __syncthreads();
 }
@@ -607,6 +618,18 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
 struct NoScatter {
   char unused;
 };
+// ACC = EmitEntries: no scatter either, but every in-range point files a 16-byte entry {row, lw, lh, attention weight}
+// under its bilinear cell for the sorted deterministic path (msda_det.cuh) -- this replaces that path's separate fill
+// pass (which re-read every location / weight and redid the coordinate arithmetic) with one cursor atomic and one
+// 16-byte store per point issued from the lane that has just built the point's record.
+struct EmitEntries {
+  char unused[3];
+};
+struct EmitArgs {
+  int* cursor;            // [bins] zero-initialised fill counters
+  const int* bin_start;   // [bins + 1] exclusive scan of the per-bin counts
+  int4* entries;          // [points in range]
+};
 
 __device__ __forceinline__ void scatter4(float* g, const float c, const float4 go, float /*scale*/) {
   // red (no return value) on purpose: atomicAdd(float4*) may compile to ATOM.E.ADD.F32x4 with a dead
@@ -719,10 +742,12 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
                      const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
                      const float* __restrict__ loc, const float* __restrict__ w,
                      ACC* __restrict__ grad_value, float* __restrict__ grad_loc,
-                     float* __restrict__ grad_w, const DetScale* __restrict__ det, const FusedArgs fused, int B,
-                     int S, int H, int L, int Q, int P, int64_t rows) {
+                     float* __restrict__ grad_w, const DetScale* __restrict__ det, const FusedArgs fused,
+                     const EmitArgs emit, int B, int S, int H, int L, int Q, int P, int64_t rows) {
   // FUSED: loc = raw offsets, w = logits in; grad_loc = grad of the offsets, grad_w = grad of the logits out
   static_assert(THREADS <= 256, "single-pass CTAs");
+  constexpr bool EMIT = sizeof(ACC) == sizeof(EmitEntries);
+  static_assert(!EMIT || (ORDER == 0 && PRE == kPrePlain), "entries are emitted by the plain LINEAR backward");
   constexpr int DL = D * 4 / CPL;
   using G = Geom<DL, THREADS>;
   constexpr int LANES = G::LANES;
@@ -769,7 +794,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     }
     if constexpr (FUSED)
       early_sum = row_softmax<LANES, 4>(w + cur.row * (int64_t)NP, reinterpret_cast<float*>(s_fin) + 3, NP, sub);
-    load_levels_plain(tab, shapes, lsi, L);
+    load_levels_plain<EMIT>(tab, shapes, lsi, L);
   } else {
     if constexpr (DCN) set_single_level<G::TW, G::TH>(tab, fused.height_in, fused.width_in);
     else if constexpr (ORDER == 0 || ORDER == 2) load_levels_plain(tab, shapes, lsi, L);
@@ -801,6 +826,15 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           if constexpr (DCN) {
             const float2 px = dcn_location(xy, pt, (int)((cur.row / H) % Q), fused);
             r = record_from_cell(locate_pixel(px.x, px.y, tab->H[0], tab->W[0]), aw, tab->H[0], tab->W[0], 0, H, cur.h, D);
+          } else if constexpr (EMIT) {
+            const Cell<float> c = locate<float>(xy.x, xy.y, tab->H[l], tab->W[l]);
+            r = record_from_cell(c, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+            if (c.valid != 0u) {   // same bin index as det_bin_kernel (msda_det.cuh): cells of the extended grid
+              const int bin = (cur.b * H + cur.h) * tab->cells_per_bh + tab->cell_begin[l] +
+                              (c.y0 + 1) * (tab->W[l] + 1) + (c.x0 + 1);
+              const int pos = __ldg(emit.bin_start + bin) + atomicAdd(emit.cursor + bin, 1);
+              emit.entries[pos] = make_int4((int)cur.row, __float_as_int(c.lw), __float_as_int(c.lh), __float_as_int(aw));
+            }
           } else {
             r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
           }
@@ -832,7 +866,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     __syncwarp();
 
     constexpr bool DET = sizeof(ACC) == 8;
-    constexpr bool SCATTER = sizeof(ACC) != sizeof(NoScatter);
+    constexpr bool SCATTER = sizeof(ACC) != sizeof(NoScatter) && !EMIT;
     static_assert(!(sizeof(ACC) == 8 && CPL != 4), "the fixed-point red path transposes 4 channels per lane");
     const int64_t img = (int64_t)cur.b * S * HD + sub * CPL;
     const VT* vimg = value + img;

@@ -54,7 +54,8 @@ int launch_fwd_fast(cudaStream_t st, const Dims& d, const void* value, const int
 template <int D, typename VT, int PT, int THREADS, int ORDER, typename ACC, int PRE = 0>
 int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* value, const int64_t* shapes,
                     const int64_t* lsi, const void* loc, const void* w, ACC* gv, void* gl, void* gw,
-                    const msda::DetScale* det, msda::FusedArgs fa = msda::FusedArgs{}) {
+                    const msda::DetScale* det, msda::FusedArgs fa = msda::FusedArgs{},
+                    msda::EmitArgs emit = msda::EmitArgs{}) {
   // The backward keeps 4 channels per lane for every type: it is bound by the grad_value reds, and those run
   // fastest as one full 128-byte line per row and instruction (8 channels per lane -> two 64-byte halves per
   // row: 1.75 -> 2.09 ms at cfg2 with bf16 value), so the faster 16-byte gather buys nothing there.
@@ -69,7 +70,7 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
   if (ORDER == 2) grid = (unsigned)((int64_t)d.B * d.H * ((d.Q + G::RPC - 1) / G::RPC));
   if (ORDER == 3) grid = (unsigned)((int64_t)d.B * d.H * tile2d_bound(d, G::RPC));
   k<<<grid, THREADS, smem, st>>>((const VT*)go, (const VT*)value, shapes, lsi, (const float*)loc, (const float*)w,
-                                 gv, (float*)gl, (float*)gw, det, fa, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
+                                 gv, (float*)gl, (float*)gw, det, fa, emit, d.B, d.S, d.H, d.L, d.Q, d.P, rows);
   count_launch();
   MSDA_CUDA(cudaGetLastError());
   return MSDA_OK;

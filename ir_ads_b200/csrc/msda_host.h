@@ -70,6 +70,9 @@ int bwd_fast_det(cudaStream_t st, const Dims& d, int dtype, const void* go, cons
                  const msda::DetScale* det);
 int bwd_fast_noscatter(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value,
                        const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, void* gl, void* gw);
+int bwd_fast_emit(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
+                  const int64_t* lsi, const void* loc, const void* w, void* gl, void* gw, int* cursor,
+                  const int* bin_start, void* entries);
 int bwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
               const int64_t* lsi, const void* off, const void* logits, float* gv, void* goff, void* glog,
               msda::FusedArgs fa);

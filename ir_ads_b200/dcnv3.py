@@ -7,8 +7,12 @@ input / offset / mask.  DCNv3 is MSDeformAttn with one level, K = kernel_h*kerne
 positions come from a convolution-style grid, and groups in the role of heads -- so it runs on the
 same kernels with a different record-building phase (ir_ads_b200/csrc/msda_fast.cuh, PRE == 2).
 
-Supported here: group_channels in {16, 32, 64, 128}, K <= 64, float32 / bfloat16 input (float16 is
-widened like the reference's custom_fwd would keep it); anything else raises (no fallback).
+Fast path: group_channels in {16, 32, 64, 128}, K <= 64, float32 / bfloat16 input (float16 is widened to float32
+around the op).  Every other shape / dtype the reference dispatches (any channel count, float64:
+detrex/layers/csrc/DCNv3/dcnv3_cuda.cu:66-80 uses AT_DISPATCH_FLOATING_TYPES_AND_HALF) runs as a composition on the
+GENERIC MSDeformAttn kernels (csrc/msda_generic.cuh, any D, float32 / float64): the convolution-grid sampling positions
+are formed with the reference kernel's arithmetic in PyTorch, normalised, and handed to
+MultiScaleDeformableAttnFunction with one level -- still CUDA only, still no CPU path.
 """
 from __future__ import annotations
 
@@ -87,6 +91,45 @@ def dcnv3_backward(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, 
     return [grad_input, grad_offset, grad_mask]
 
 
+def fast_supported(input: torch.Tensor, kernel_h: int, kernel_w: int, group_channels: int) -> bool:
+    """The shapes / dtypes the DCN record mode of the fast kernels covers."""
+    return (group_channels in (16, 32, 64, 128) and 1 <= kernel_h * kernel_w <= 64
+            and input.dtype in (torch.float32, torch.bfloat16, torch.float16))
+
+
+def dcnv3_composed(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
+                   group, group_channels, offset_scale) -> torch.Tensor:
+    """DCNv3 as ONE-LEVEL MSDeformAttn on the generic kernels, differentiable through autograd.  Sampling position of
+    kernel point (i, j) for output pixel (ho, wo), in input-pixel units (dcnv3_im2col_cuda.cuh:232-260):
+        x = (cw - pad_w + wo*stride_w) - cw*scale + (i*dil_w + off_x)*scale,   cw = dil_w*(kernel_w-1)//2   (y alike)
+    MSDeformAttn samples at loc*size - 0.5, so loc = (x + 0.5) / W_in."""
+    from .functional import MultiScaleDeformableAttnFunction
+    _require(input.is_cuda, "Not implemented on the CPU")
+    N, H_in, W_in, C = input.shape
+    _, H_out, W_out, _ = offset.shape
+    K = kernel_h * kernel_w
+    _require(C == group * group_channels, f"input channels {C} != group*group_channels {group * group_channels}")
+    _require(tuple(offset.shape) == (N, H_out, W_out, group * K * 2), "offset must be [N, H_out, W_out, group*K*2]")
+    _require(tuple(mask.shape) == (N, H_out, W_out, group * K), "mask must be [N, H_out, W_out, group*K]")
+    cdt = torch.float64 if input.dtype == torch.float64 else torch.float32
+    dev = input.device
+    value = input.to(cdt).reshape(N, H_in * W_in, group, group_channels)
+    off = offset.to(cdt).reshape(N, H_out, W_out, group, K, 2)
+    cw, ch = (dilation_w * (kernel_w - 1)) // 2, (dilation_h * (kernel_h - 1)) // 2
+    pt = torch.arange(K, device=dev)
+    i, j = (pt // kernel_h).to(cdt), (pt % kernel_h).to(cdt)                 # point index = i*kernel_h + j, i over kernel_w
+    wo = torch.arange(W_out, device=dev, dtype=cdt).view(1, 1, W_out, 1, 1)
+    ho = torch.arange(H_out, device=dev, dtype=cdt).view(1, H_out, 1, 1, 1)
+    x = (cw - pad_w + wo * stride_w) - cw * offset_scale + (i * dilation_w + off[..., 0]) * offset_scale
+    y = (ch - pad_h + ho * stride_h) - ch * offset_scale + (j * dilation_h + off[..., 1]) * offset_scale
+    loc = torch.stack([(x + 0.5) / W_in, (y + 0.5) / H_in], -1).reshape(N, H_out * W_out, group, 1, K, 2)
+    w = mask.to(cdt).reshape(N, H_out * W_out, group, 1, K)
+    shapes = torch.tensor([[H_in, W_in]], dtype=torch.long, device=dev)
+    lsi = torch.zeros(1, dtype=torch.long, device=dev)
+    out = MultiScaleDeformableAttnFunction.apply(value.contiguous(), shapes, lsi, loc.contiguous(), w.contiguous(), 64)
+    return out.reshape(N, H_out, W_out, C).to(input.dtype)
+
+
 class DCNv3Function(Function):
     """Same 15-argument ``apply`` as the reference (dcn_v3.py:21-65)."""
 
@@ -97,6 +140,14 @@ class DCNv3Function(Function):
                     offset_scale)
         ctx.im2col_step = im2col_step
         ctx.in_dtype = input.dtype
+        ctx.composed = None
+        if not fast_supported(input, kernel_h, kernel_w, group_channels):
+            # any other channel count / float64: the composition on the generic kernels, graph kept for backward
+            with torch.enable_grad():
+                leaves = [t.detach().requires_grad_(True) for t in (input, offset, mask)]
+                out = dcnv3_composed(*leaves, *ctx.args)
+            ctx.composed = (leaves, out)
+            return out.detach()
         if input.dtype == torch.float16:
             input = input.float()
         output = dcnv3_forward(input, offset.float(), mask.float(), *ctx.args, im2col_step)
@@ -106,6 +157,10 @@ class DCNv3Function(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
+        if ctx.composed is not None:
+            leaves, out = ctx.composed
+            ctx.composed = None
+            return tuple(torch.autograd.grad(out, leaves, grad_output.to(out.dtype))) + (None,) * 12
         input, offset, mask = ctx.saved_tensors
         gi, go, gm = dcnv3_backward(input, offset.float(), mask.float(), *ctx.args, grad_output.to(input.dtype),
                                     ctx.im2col_step)

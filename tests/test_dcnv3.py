@@ -91,8 +91,7 @@ def test_kernels_match_reference_golden(golden, name, dtype):
 
 @pytest.mark.gpu
 def test_dcnv3_larger_shape_and_unsupported():
-    """InternImage-like stage (56x56, 4 groups x 16 channels, 3x3) against the port in float64; an unsupported
-    channel count raises instead of falling back."""
+    """InternImage-like stage (56x56, 4 groups x 16 channels, 3x3) against the port in float64."""
     from ir_ads_b200.dcnv3 import DCNv3Function
     dev = "cuda:0"
     g = torch.Generator().manual_seed(0)
@@ -109,9 +108,46 @@ def test_dcnv3_larger_shape_and_unsupported():
     for gt, w, key in zip([out, leaves[0].grad, leaves[2].grad], [want[0], want[1], want[3]], ("out", "grad_input", "grad_mask")):
         err = (gt.detach().double().cpu() - w).abs().max().item()
         assert err <= 1e-5 * w.abs().max().item() + 1e-6, (key, err)
-    with pytest.raises(RuntimeError, match="UNSUPPORTED"):
-        DCNv3Function.apply(torch.randn(1, 4, 4, 2 * 24, device=dev), torch.zeros(1, 4, 4, 36, device=dev),
-                            torch.ones(1, 4, 4, 18, device=dev), 3, 3, 1, 1, 1, 1, 1, 1, 2, 24, 1.0, 256)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16])
+@pytest.mark.parametrize("C,k,stride,pad,dil,scale", [(24, 3, 1, 1, 1, 1.0), (8, 3, 2, 1, 1, 2.0), (40, 5, 1, 2, 1, 0.7),
+                                                      (12, 3, 1, 2, 2, 1.0), (16, 9, 1, 4, 1, 1.0)])
+def test_dcnv3_generic_shapes_against_port(C, k, stride, pad, dil, scale, dtype):
+    """Channel counts outside {16,32,64,128}, K > 64 (9x9 = 81 points) and float64 -- everything else the reference
+    dispatches (dcnv3_cuda.cu:66-80) -- run as a one-level MSDeformAttn composition on the generic kernels; checked
+    against the float64 port of dcnv3_core_pytorch, all four tensors."""
+    from ir_ads_b200.dcnv3 import DCNv3Function, fast_supported
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(C + k)
+    N, H, W, G = 2, 13, 17, 3
+    K = k * k
+    Ho = (H + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    inp = torch.randn(N, H, W, G * C, generator=g)
+    off = torch.randn(N, Ho, Wo, G * K * 2, generator=g) * 1.5
+    mask = torch.softmax(torch.randn(N, Ho, Wo, G, K, generator=g), -1).reshape(N, Ho, Wo, G * K)
+    go = torch.randn(N, Ho, Wo, G * C, generator=g)
+    args = (k, k, stride, stride, pad, pad, dil, dil, G, C, scale)
+    if dtype == torch.float16:
+        inp, go = inp.half().float(), go.half().float()       # yardstick on the same rounded inputs
+    assert dtype == torch.float64 or not fast_supported(inp.to(dtype), k, k, C)
+    want = dcnv3_torch.forward_backward(inp.double(), off.double(), mask.double(), go.double(), *args)
+    aux = torch.float64 if dtype == torch.float64 else torch.float32
+    leaves = [inp.to(dev, dtype).requires_grad_(True), off.to(dev, aux).requires_grad_(True),
+              mask.to(dev, aux).requires_grad_(True)]
+    out = DCNv3Function.apply(*leaves, *args, 256)
+    assert out.dtype == dtype and tuple(out.shape) == (N, Ho, Wo, G * C)
+    out.backward(go.to(dev, dtype))
+    c = {"offset": off.numpy(), "args": args}
+    m = torch.from_numpy(pixel_smooth_mask(c, 1e-4)).double()
+    tol = {torch.float64: 1e-10, torch.float32: 1e-5, torch.float16: 2e-3}[dtype]
+    for gt, w, key in zip([out, leaves[0].grad, leaves[1].grad, leaves[2].grad], want, ("out", "grad_input", "grad_offset", "grad_mask")):
+        gt = gt.detach().double().cpu()
+        mk = m if key == "grad_offset" else 1.0
+        err = ((gt - w) * mk).abs().max().item()
+        assert err <= tol * w.abs().max().item() + 1e-6, (key, err, w.abs().max().item())
 
 
 @pytest.mark.gpu
