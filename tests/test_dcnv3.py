@@ -142,7 +142,9 @@ def test_dcnv3_generic_shapes_against_port(C, k, stride, pad, dil, scale, dtype)
     out.backward(go.to(dev, dtype))
     c = {"offset": off.numpy(), "args": args}
     m = torch.from_numpy(pixel_smooth_mask(c, 1e-4)).double()
-    tol = {torch.float64: 1e-10, torch.float32: 1e-5, torch.float16: 2e-3}[dtype]
+    # (the port, like the reference function it restates, builds its reference points and dilation grid in float32 --
+    # dcn_v3.py:74-118 -- so even the float64 run agrees with it to float32 location accuracy only)
+    tol = {torch.float64: 1e-5, torch.float32: 1e-5, torch.float16: 2e-3}[dtype]
     for gt, w, key in zip([out, leaves[0].grad, leaves[1].grad, leaves[2].grad], want, ("out", "grad_input", "grad_offset", "grad_mask")):
         gt = gt.detach().double().cpu()
         mk = m if key == "grad_offset" else 1.0
