@@ -93,9 +93,10 @@ msda_bwd_fold_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
   const int64_t n_items = (int64_t)BH * tab->total_tiles;
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     // ---- work item -> (tile, image, head) ----
-    const unsigned it = (unsigned)item;
-    const unsigned t = it / (unsigned)BH, bh = it - t * (unsigned)BH;
-    const int b = (int)(bh / (unsigned)H), h = (int)(bh - (unsigned)b * (unsigned)H);
+    const unsigned it = (unsigned)item, per_img = (unsigned)H * (unsigned)tab->total_tiles;   // image slowest (L2)
+    const unsigned bb = it / per_img, rem = it - bb * per_img;
+    const unsigned t = rem / (unsigned)H;
+    const int b = (int)bb, h = (int)(rem - t * (unsigned)H);
     int lq = 0;
 #pragma unroll 1
     for (int k = 1; k < L; ++k)
