@@ -79,6 +79,7 @@ CASES = [
     ("cfg2_B8_test_dist", "cfg2", 8, "test", "default"),
     ("cfg3_bf16_B8", "cfg3", 8, "model", "default"),
     ("cfg3_bf16_B8_edge", "cfg3", 8, "edge", "default"),
+    ("cfg2_bf16_B8", "cfg2_bf16", 8, "model", "default"),
     ("cfg3_f32_B8", "cfg3_f32", 8, "model", "default"),
     ("cfg4_B2", "cfg4", 2, "model", "default"),
     ("cfg5_det_B8", "cfg5", 8, "model", "deterministic"),
