@@ -10,8 +10,9 @@ encoder's self-attention, 6 layers, batch 8 @ 800x1333 (levels 100x167, 50x84, 2
 Q = S = 22223, 8 heads x 32 channels, 4 points), fp32.  One STEP = the core op's forward and
 backward for all 6 layers (6 distinct input sets, ~1.3 GB each, so nothing survives in the 126 MB
 L2 between uses).  N > 1 shards by image batch (weak scaling, 8 images per GPU, no collective
-inside the op) and adds the training config's NCCL all-reduce of the 6 modules' projection-weight
-gradients per step.
+inside the op; nothing is exchanged).  `--scaling strong --total-batch N` splits a fixed batch over the
+GPUs; `--mode train` is BASELINE config 4, the batch-sharded training step: 6 MSDeformAttn modules forward +
+backward, per-module NCCL all-reduce of the projection-weight gradients launched from gradient hooks, fused AdamW.
 
   value     points/s with inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       the same through the public autograd API with HOST buffers: pinned host -> device copies
@@ -81,8 +82,8 @@ def config_dict(wl, args, extra=None):
         "l2_hygiene": f"{args.layers} distinct layer input sets cycled per step "
                       f"({wl.algorithmic_bytes()[0] / 1e6:.0f} MB of inputs each"
                       f"{', larger than the 126 MB L2' if wl.batch >= 4 else '; plus an L2 flush (256 MB write) between timed regions'})",
-        "parallelism": f"image-batch sharding x{args.gpus}, no collective inside the op"
-                       + ("; per step one NCCL mean all-reduce of the projection-weight grads (5.5 MB)" if args.gpus > 1 else ""),
+        "parallelism": f"image-batch sharding x{args.gpus}, no collective inside or around the core op (NCCL: barrier and "
+                       "max-over-ranks of the step time only; the training config's gradient all-reduce is in --mode train)",
         "scaling_mode": args.scaling, "total_batch": wl.batch * args.gpus,
     }
     if extra:
@@ -327,19 +328,8 @@ def main():
         layers.append((value, shapes, lsi, loc, w, go))
     # small per-GPU batches (strong scaling) fit in L2: flush it between timed regions
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if wl.batch < 4 else None
-    # the training config's exchange step: mean all-reduce of the L modules' projection-weight grads.  In this (core
-    # operator) mode no projection runs, so the payload is the right size but synthetic; --mode train exchanges the
-    # gradients a real module backward produced, overlapped with it.
-    bucket = None
-    if dist_on:
-        from ir_ads_b200 import MultiScaleDeformableAttention, sharding
-        mods = [MultiScaleDeformableAttention(wl.num_heads * wl.head_dim, wl.num_heads, wl.num_levels,
-                                              wl.num_points).to(dev) for _ in range(L)]
-        params = sharding.projection_parameters(mods)
-        for p in params:
-            p.grad = torch.ones_like(p)
-        bucket = sharding.GradBucket(params)
-
+    # No collective in this mode: the core operator shards by image and exchanges nothing.  The
+    # training config's gradient all-reduce is measured where real gradients exist: --mode train.
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(record=None):
@@ -355,8 +345,6 @@ def main():
                 e2.record()
                 record.append((e0, e1, e2))
             del out
-        if dist_on:
-            bucket.all_reduce_mean()
 
     def barrier():
         if dist_on:
