@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Builds and runs the two stand-alone microbenchmarks behind bench.py's `roofline.onchip` block and writes
+profiles/microbench_ceilings.json (needs nvcc + a B200; ~30 s):
+
+  gather_v8.cu    91.0 M corner rows of 128 B gathered with 8 lanes x LDG.E.128 (the forward / backward gather pattern),
+                  windows of 64 lines (L1 resident), 2048 lines and 131072 lines (16 MB: L2 sourced)
+  red_vs_tma.cu   22.8 M rows of 128 B added with 8 lanes x red.global.add.v4.f32 (the backward scatter pattern) into
+                  L2-resident windows; scaled x4 to the 91.0 M rows of one cfg2 layer
+
+Usage: python tools/microbench/run_ceilings.py [out.json]"""
+import json
+import os
+import re
+import subprocess
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+BUILD = os.path.join(ROOT, "build", "microbench")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3"]
+
+
+def build_and_run(name):
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, name)
+    subprocess.check_call(["nvcc", *ARCH, "-o", exe, os.path.join(HERE, name + ".cu")])
+    return subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+
+
+def main():
+    out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "microbench_ceilings.json")
+    g = build_and_run("gather_v8")
+    gather = {}
+    for m in re.finditer(r"window\s+(\d+) lines:.*?v4 \(8 lanes, LDG\.128\) ([\d.]+) ms", g):
+        gather[int(m.group(1))] = float(m.group(2))
+    r = build_and_run("red_vs_tma")
+    red = {}
+    window = None
+    for line in r.splitlines():
+        m = re.match(r"-- window (\d+) lines", line)
+        if m:
+            window = int(m.group(1))
+        m = re.match(r"A red\.v4\.f32 128B/row\s+([\d.]+) ms\s+([\d.]+) Grows/s\s+([\d.]+) TB/s", line)
+        if m and window is not None:
+            red[window] = (float(m.group(1)), float(m.group(3)))
+    rows = 91025408
+    l2_windows = [w for w in red if w <= 262144]
+    best_red_ms = min(red[w][0] for w in l2_windows)
+    res = {
+        "_comment": "On-chip ceilings of the two access patterns the MSDeformAttn kernels are made of, measured by "
+                    "tools/microbench/run_ceilings.py (gather_v8.cu, red_vs_tma.cu; CUDA events, warm).  bench.py scales "
+                    "them by the workload's corner-row count and reports them beside the HBM roofline fraction "
+                    "(roofline.onchip); the HBM fraction stays the headline.",
+        "measured": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),
+        "rows_measured": rows, "row_bytes": 128,
+        "gather_l1_resident_ms": gather[64], "gather_l2_256KB_window_ms": gather[2048], "gather_l2_sourced_ms": gather[131072],
+        "red_v4_f32_l2_resident_ms": round(best_red_ms * 4, 4),
+        "red_payload_tbs": max(red[w][1] for w in l2_windows),
+        "red_windows": {str(w): {"ms_for_22.8M_rows": red[w][0], "payload_tbs": red[w][1]} for w in sorted(red)},
+        "gather_tool": "tools/microbench/gather_v8.cu (8 lanes x LDG.E.128 per 128-byte row, 4 rows per warp instruction)",
+        "scatter_tool": "tools/microbench/red_vs_tma.cu (8 lanes x red.global.add.v4.f32 per 128-byte row; TMA bulk reduce "
+                        "gives the same rate)",
+        "raw": {"gather_v8": g.strip().splitlines(), "red_vs_tma": r.strip().splitlines()},
+    }
+    with open(out_path, "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps({k: v for k, v in res.items() if k not in ("raw", "_comment")}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
