@@ -253,10 +253,12 @@ def ncu_traffic(workload: str, kernel: str):
         return None
 
 
-def onchip_block(wl, fwd_ms, bwd_ms):
-    """The measured on-chip ceilings (profiles/microbench_ceilings.json) scaled to this workload's corner rows: the
-    kernels gather 4 corner rows of D channels per point through L1 and scatter as many through L2 reds; those rates,
-    not HBM, bound them.  Reported beside the HBM fraction, never instead of it."""
+def onchip_block(wl, fwd_ms, bwd_ms, valid_frac):
+    """The measured on-chip ceilings (profiles/microbench_ceilings.json) scaled to the corner rows this workload
+    actually moves: the kernels gather up to 4 corner rows of D channels per point through L1 and scatter as many
+    through L2 reds (padded corners -- `valid_frac` of the 4 * N are inside their level -- are neither loaded nor
+    scattered); those rates, not HBM, bound them.  Reported beside the HBM fraction, never
+    instead of it."""
     try:
         with open(os.path.join(ROOT, "profiles", "microbench_ceilings.json")) as f:
             c = json.load(f)
@@ -265,14 +267,13 @@ def onchip_block(wl, fwd_ms, bwd_ms):
     if wl.value_dtype != "f32" or wl.head_dim != 32:
         return None                                  # the ceilings were measured on 128-byte float rows
     rows = wl.points * 4
-    k = rows / c["rows_measured"]
+    k = rows * valid_frac / c["rows_measured"]
     g1, g2, red = c["gather_l1_resident_ms"] * k, c["gather_l2_sourced_ms"] * k, c["red_v4_f32_l2_resident_ms"] * k
-    return {"corner_rows_per_launch": rows, "row_bytes": c["row_bytes"],
+    return {"corner_rows_per_launch": rows, "corner_rows_inside_the_map": int(rows * valid_frac), "row_bytes": c["row_bytes"],
             "ceilings_ms": {"fwd_gather_l1_resident": g1, "fwd_gather_l2_sourced": g2, "bwd_red_l2_rate": red},
             "fwd_frac_of_onchip_ceiling": g2 / fwd_ms, "bwd_frac_of_onchip_ceiling": red / bwd_ms,
             "ncu_counters_cfg2": c.get("ncu_counters_cfg2"),
-            "note": "ceiling / measured launch time; > 1 is possible for the backward because ~14 % of the corners of "
-                    "model-like inputs carry weight 0 (padding) and issue no red",
+            "note": "ceiling for the rows inside the map / measured launch time (backward: incl. its grad_value zero-fill)",
             "source": "profiles/microbench_ceilings.json (tools/microbench/*.cu on this pool's B200s)"}
 
 
@@ -418,7 +419,8 @@ def main():
                 "fwd": {"algorithmic_bytes_per_launch": fwd_bytes, "launch_ms": fwd_ms,
                         "achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "frac": fwd_bytes / (fwd_ms * 1e-3) / 1e9 / peak},
                 "fwd_bwd_frac": (fwd_bytes + bwd_bytes) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak}
-        oc = onchip_block(wl, fwd_ms, bwd_ms) if not wl.deterministic else None
+        from ir_ads_b200.workloads import valid_corner_fraction
+        oc = onchip_block(wl, fwd_ms, bwd_ms, valid_corner_fraction(layers[0][3], wl.levels)) if not wl.deterministic else None
         if oc is not None:
             roof["onchip"] = oc
         line = {

@@ -87,9 +87,9 @@ int check_dims(const Dims& d, int dtype) {
 }
 
 // Test hook (msda_debug_bookkeeping with MSDA_DEBUG_FAST_RECORDS): builds the SAME PointRec the fast kernels build
-// (msda::make_record: locate + clamp + alias flags) and decodes it the way their gather loops do -- o00 = oc & ~15,
-// +H*D if bit0, +W_l*H*D if bit1; corner validity as the backward's finalize step derives it from bits 2/3 -- so
-// the integers the fast kernels actually gather from / scatter to are what the test compares bit for bit.
+// (msda::make_record: locate + unclamped offset + corner-validity bits) and decodes it the way their gather / scatter
+// loops do -- o00 = oc & ~15, +H*D for x+1, +W_l*H*D for y+1, corner k used iff bit k -- so the integers the fast
+// kernels actually gather from / scatter to are what the test compares bit for bit.
 __global__ void msda_fast_records_kernel(const float* __restrict__ loc, const int64_t* __restrict__ shapes,
                                          const int64_t* __restrict__ lsi, int S, int H, int D, int L, int Q, int P,
                                          int64_t npts, int64_t* __restrict__ offs, float* __restrict__ frac) {
@@ -101,18 +101,15 @@ __global__ void msda_fast_records_kernel(const float* __restrict__ loc, const in
     const int64_t b = row / H / Q;
     const int Hl = (int)shapes[2 * l], Wl = (int)shapes[2 * l + 1];
     const msda::PointRec r = msda::make_record(loc[2 * pt], loc[2 * pt + 1], 1.0f, Hl, Wl, (int)lsi[l], H, h, D);
-    const bool gated = r.lw < 0.0f;
     const int oc = r.oc;
+    const bool gated = (oc & 15) == 0;
     const int o00 = oc & ~15;
-    const int o01 = o00 + ((oc & 1) ? HD : 0);
-    const int dy = (oc & 2) ? Wl * HD : 0;
-    const bool x0v = (oc & 4) != 0, y0v = (oc & 8) != 0;
-    const bool x1v = (oc & 1) != 0 || !x0v, y1v = (oc & 2) != 0 || !y0v;
+    const int o01 = o00 + HD, o10 = o00 + Wl * HD, o11 = o10 + HD;
     const int64_t img = b * (int64_t)S * HD;
-    offs[4 * pt + 0] = (!gated && x0v && y0v) ? img + o00 : -1;
-    offs[4 * pt + 1] = (!gated && x1v && y0v) ? img + o01 : -1;
-    offs[4 * pt + 2] = (!gated && x0v && y1v) ? img + o00 + dy : -1;
-    offs[4 * pt + 3] = (!gated && x1v && y1v) ? img + o01 + dy : -1;
+    offs[4 * pt + 0] = (oc & 1) ? img + o00 : -1;
+    offs[4 * pt + 1] = (oc & 2) ? img + o01 : -1;
+    offs[4 * pt + 2] = (oc & 4) ? img + o10 : -1;
+    offs[4 * pt + 3] = (oc & 8) ? img + o11 : -1;
     frac[2 * pt] = gated ? 0.0f : r.lw;
     frac[2 * pt + 1] = gated ? 0.0f : r.lh;
   }

@@ -104,6 +104,55 @@ __device__ __forceinline__ Vec<N> ldv(const __nv_bfloat16* p) {
   }
   return r;
 }
+// The bits of one lane load, converted to floats only where they are consumed (the forward keeps several
+// predicated loads in flight; holding them as packed bf16 keeps the kernel inside its register budget).
+template <int N, typename VT>
+struct Raw;
+template <>
+struct Raw<4, float> {
+  float4 r;
+};
+template <>
+struct Raw<4, __nv_bfloat16> {
+  uint2 r = {0u, 0u};
+};
+template <>
+struct Raw<8, __nv_bfloat16> {
+  uint4 r = {0u, 0u, 0u, 0u};
+};
+template <int N>
+__device__ __forceinline__ Raw<N, float> ldraw(const float* p) {
+  static_assert(N == 4, "float rows use 4 channels per lane");
+  Raw<4, float> x;
+  x.r = __ldg(reinterpret_cast<const float4*>(p));
+  return x;
+}
+template <int N>
+__device__ __forceinline__ Raw<N, __nv_bfloat16> ldraw(const __nv_bfloat16* p) {
+  Raw<N, __nv_bfloat16> x;
+  if constexpr (N == 4) x.r = __ldg(reinterpret_cast<const uint2*>(p));
+  else x.r = __ldg(reinterpret_cast<const uint4*>(p));
+  return x;
+}
+__device__ __forceinline__ Vec<4> unpack(const Raw<4, float>& x) {
+  Vec<4> r;
+  r.v[0] = x.r.x; r.v[1] = x.r.y; r.v[2] = x.r.z; r.v[3] = x.r.w;
+  return r;
+}
+__device__ __forceinline__ Vec<4> unpack(const Raw<4, __nv_bfloat16>& x) {
+  Vec<4> r;
+  r.v[0] = __uint_as_float(x.r.x << 16); r.v[1] = __uint_as_float(x.r.x & 0xffff0000u);
+  r.v[2] = __uint_as_float(x.r.y << 16); r.v[3] = __uint_as_float(x.r.y & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ Vec<8> unpack(const Raw<8, __nv_bfloat16>& x) {
+  Vec<8> r;
+  r.v[0] = __uint_as_float(x.r.x << 16); r.v[1] = __uint_as_float(x.r.x & 0xffff0000u);
+  r.v[2] = __uint_as_float(x.r.y << 16); r.v[3] = __uint_as_float(x.r.y & 0xffff0000u);
+  r.v[4] = __uint_as_float(x.r.z << 16); r.v[5] = __uint_as_float(x.r.z & 0xffff0000u);
+  r.v[6] = __uint_as_float(x.r.w << 16); r.v[7] = __uint_as_float(x.r.w & 0xffff0000u);
+  return r;
+}
 template <int N>
 __device__ __forceinline__ void stv(float* p, const Vec<N>& a) {
   static_assert(N == 4, "float rows use 4 channels per lane");
@@ -306,18 +355,21 @@ struct RowWalk {
 };
 
 // ---- per-point record --------------------------------------------------------------------------
-// Every corner ADDRESS in a record is valid (coordinates clamped into the map), so the gather loop
-// has no predicates, no zero-fills and no branches; zero padding lives in the WEIGHTS (exactly 0 for
-// a padded corner or a gated-out point).  oc = element offset of the clamped low corner inside the
-// image (a multiple of 16) with four flag bits:
-//   bit0  the x+1 corner is a distinct pixel (else it aliases the low one and carries weight 0)
-//   bit1  same for y+1
-//   bit2  x0 inside the map      bit3  y0 inside the map        (backward's finalize step only)
+// oc = element offset, inside the image, of the bilinear cell's (x0, y0) corner -- NOT clamped: it lies outside the
+// map when that corner is padded, and is then never dereferenced -- with four corner-validity bits in its low bits
+// (the offset is a multiple of D >= 16):
+//   bit k  corner k = (x0 + (k & 1), y0 + (k >> 1)) is inside the map (and, in the fused module path, not under the
+//          padding mask); k: 0=(y0,x0) 1=(y0,x0+1) 2=(y0+1,x0) 3=(y0+1,x0+1)   (v1..v4 of cuh:56-80)
+// The corner offsets are oc, oc + H*D, oc + W_l*H*D, oc + (W_l+1)*H*D: no selects in the loops.  A corner whose bit
+// is clear is NOT LOADED (the loads are predicated on the bits), exactly as the reference's per-corner bounds checks
+// skip it (cuh:56-80): it costs no L1 data-pipe wavefront -- on model-like inputs ~14 % of all corners are padded --
+// and a non-finite value in a pixel that is padded or masked for this point cannot leak into the result.  All bits
+// clear = the point is gated out (cuh:288) and contributes nothing.
 struct PointRec {
-  float4 cw;   // corner weights (v1..v4 of cuh:56-80) x attention weight, 0 where padded
+  float4 cw;     // corner weights (v1..v4 of cuh:56-80) x attention weight, exactly 0 where the bit is clear
   int oc;
-  int pix;       // pixel index (inside the image) of the clamped low corner: oc == ((pix*H + h)*D) | flags
-  float lw, lh;  // fractional parts; lw < 0 marks a gated-out point
+  int pix;       // pixel index (inside the image) of the (x0, y0) corner, not clamped: oc == ((pix*H + h)*D) | bits
+  float lw, lh;  // fractional parts
 };
 
 // DCNv3 gives pixel coordinates directly (cuh:262-263 gate, :48-58 cell), no exact-product trick needed.
@@ -339,32 +391,24 @@ __device__ __forceinline__ Cell<float> locate_pixel(float px, float py, int H, i
   return c;
 }
 
-__device__ __forceinline__ PointRec record_from_cell(const Cell<float> c, float aw, int Hl, int Wl, int start, int H,
-                                                     int h, int D);
-
-__device__ __forceinline__ PointRec make_record(float x, float y, float aw, int Hl, int Wl, int start, int H, int h,
-                                                int D) {
-  return record_from_cell(locate<float>(x, y, Hl, Wl), aw, Hl, Wl, start, H, h, D);
-}
-
-__device__ __forceinline__ PointRec record_from_cell(const Cell<float> c, float aw, int Hl, int Wl, int start, int H,
-                                                     int h, int D) {
+__device__ __forceinline__ PointRec record_from_cell(const Cell<float> c, float aw, int Wl, int start, int H, int h,
+                                                     int D) {
   PointRec r;
   const float hh = 1.0f - c.lh, hw = 1.0f - c.lw;
   r.cw.x = (c.valid & 1u) ? hh * hw * aw : 0.0f;
   r.cw.y = (c.valid & 2u) ? hh * c.lw * aw : 0.0f;
   r.cw.z = (c.valid & 4u) ? c.lh * hw * aw : 0.0f;
   r.cw.w = (c.valid & 8u) ? c.lh * c.lw * aw : 0.0f;
-  const bool gated = c.valid == 0u;
-  const bool x0v = c.x0 >= 0, x1v = c.x0 + 1 <= Wl - 1, y0v = c.y0 >= 0, y1v = c.y0 + 1 <= Hl - 1;
-  const int xc = gated ? 0 : max(c.x0, 0), yc = gated ? 0 : max(c.y0, 0);
-  int flags = 0;
-  if (!gated) flags = (int)(x0v && x1v) | ((int)(y0v && y1v) << 1) | ((int)x0v << 2) | ((int)y0v << 3);
-  r.pix = start + yc * Wl + xc;
-  r.oc = ((r.pix * H + h) * D) | flags;
-  r.lw = gated ? -1.0f : c.lw;
+  r.pix = (c.valid == 0u) ? 0 : start + c.y0 * Wl + c.x0;
+  r.oc = ((r.pix * H + h) * D) | (int)c.valid;
+  r.lw = c.lw;
   r.lh = c.lh;
   return r;
+}
+
+__device__ __forceinline__ PointRec make_record(float x, float y, float aw, int Hl, int Wl, int start, int H, int h,
+                                                int D) {
+  return record_from_cell(locate<float>(x, y, Hl, Wl), aw, Wl, start, H, h, D);
 }
 
 // ---- fused pre-op chain -----------------------------------------------------
@@ -409,26 +453,20 @@ __device__ __forceinline__ float2 fused_location(const float2 off, const float* 
   return loc;
 }
 
-// Padding mask folded into the records.  A masked pixel's value row counts as zeros, so its corner weight becomes
-// zero: the forward then adds nothing for it and the backward scatters nothing into it (grad_value of a masked
-// pixel stays 0, which is masked_fill's own backward).  Backward's finalize step must also treat that corner's
-// VALUE as 0 in grad_sampling_loc / grad_attn_weight, whereas a corner whose weight merely happens to be 0
-// (lw == 0, say) still enters the location gradient.  The two are told apart by the zero's sign: masked corners
-// carry -0.0f, every other zero weight is canonicalised to +0.0f (x + 0.0f maps -0 to +0 and nothing else).
-// The row is still loaded, so a non-finite value under the mask would propagate (the reference's masked_fill
-// discards it); values there come out of value_proj and are finite.
+// Padding mask folded into the records.  A masked pixel's value row counts as zeros: the corner's validity bit is
+// cleared and its weight set to 0, so the forward neither loads it nor adds anything for it, the backward scatters
+// nothing into it (grad_value of a masked pixel stays 0, which is masked_fill's own backward) and drops its value
+// from grad_sampling_loc / grad_attn_weight -- whereas a corner whose weight merely happens to be 0 (lw == 0, say)
+// keeps its bit and still enters the location gradient.  Only the mask bytes of in-map corners are read.
 __device__ __forceinline__ void apply_value_mask(PointRec& r, const unsigned char* mask_img, int Wl) {
-  const int dx = r.oc & 1, dy = (r.oc & 2) ? Wl : 0;
-  const bool m00 = __ldg(mask_img + r.pix) != 0, m01 = __ldg(mask_img + r.pix + dx) != 0;
-  const bool m10 = __ldg(mask_img + r.pix + dy) != 0, m11 = __ldg(mask_img + r.pix + dy + dx) != 0;
-  r.cw.x = m00 ? -0.0f : __fadd_rn(r.cw.x, 0.0f);
-  r.cw.y = m01 ? -0.0f : __fadd_rn(r.cw.y, 0.0f);
-  r.cw.z = m10 ? -0.0f : __fadd_rn(r.cw.z, 0.0f);
-  r.cw.w = m11 ? -0.0f : __fadd_rn(r.cw.w, 0.0f);
-}
-__device__ __forceinline__ unsigned masked_corners(const float4 cw) {
-  return (unsigned)(__float_as_uint(cw.x) == 0x80000000u) | ((unsigned)(__float_as_uint(cw.y) == 0x80000000u) << 1) |
-         ((unsigned)(__float_as_uint(cw.z) == 0x80000000u) << 2) | ((unsigned)(__float_as_uint(cw.w) == 0x80000000u) << 3);
+  const int v = r.oc & 15;
+  const bool k0 = (v & 1) && __ldg(mask_img + r.pix) == 0, k1 = (v & 2) && __ldg(mask_img + r.pix + 1) == 0;
+  const bool k2 = (v & 4) && __ldg(mask_img + r.pix + Wl) == 0, k3 = (v & 8) && __ldg(mask_img + r.pix + Wl + 1) == 0;
+  r.cw.x = k0 ? r.cw.x : 0.0f;
+  r.cw.y = k1 ? r.cw.y : 0.0f;
+  r.cw.z = k2 ? r.cw.z : 0.0f;
+  r.cw.w = k3 ? r.cw.w : 0.0f;
+  r.oc = (r.oc & ~15) | (int)k0 | ((int)k1 << 1) | ((int)k2 << 2) | ((int)k3 << 3);
 }
 
 // DCNv3 sampling position of kernel point `pt` (= i*kernel_h + j, i over kernel_w) for output pixel q,
@@ -501,6 +539,16 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
   float* my = recs + (size_t)rin * row_words;
   float4* s_cw = reinterpret_cast<float4*>(my);
   int* s_oc = reinterpret_cast<int*>(my + 4 * NP);
+  // -DMSDA_FWD_REC16=1 (experiment, VERDICT r01 task 4): a 16-byte record {oc | validity bits, lw, (1-lh)*aw, lh*aw}
+  // whose four corner weights the gather loop forms itself (1 FADD + 4 FMUL): ONE LDS.128 per point = 2 L1 data-pipe
+  // wavefronts per point and warp instead of 3 (LDS.128 + LDS.32).  Measured with the clamped-address loop of round 1:
+  // cfg2 model 0.609 -> 0.589 ms, cfg2 test 0.566 -> 0.579 ms; with the predicated loads below it buys nothing
+  // (0.551 either way) and still costs the inputs without locality (0.583 -> 0.615 ms): off (profiles/r02j_*).
+#ifndef MSDA_FWD_REC16
+#define MSDA_FWD_REC16 0
+#endif
+  constexpr bool REC16 = MSDA_FWD_REC16 != 0;
+  int4* s_rec = reinterpret_cast<int4*>(my);             // REC16 only (s_oc stays the fused softmax's scratch)
 
   // Single-pass orders (LINEAR, STRIP) know their row without the level table, so the first locations / weights
   // of the row are requested BEFORE the table's load + barrier: the two global-memory latencies of a CTA's
@@ -554,15 +602,19 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
           PointRec r;
           if constexpr (DCN) {
             const float2 px = dcn_location(xy, pt, (int)((cur.row / H) % Q), fused);
-            r = record_from_cell(locate_pixel(px.x, px.y, tab->H[0], tab->W[0]), aw, tab->H[0], tab->W[0], 0, H, cur.h, D);
+            r = record_from_cell(locate_pixel(px.x, px.y, tab->H[0], tab->W[0]), aw, tab->W[0], 0, H, cur.h, D);
           } else {
             r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
           }
           if constexpr (FUSED) {
             if (fused.value_mask) apply_value_mask(r, fused.value_mask + (int64_t)cur.b * S, tab->W[l]);
           }
-          s_cw[pt] = r.cw;
-          s_oc[pt] = r.oc;
+          if constexpr (REC16) {
+            s_rec[pt] = make_int4(r.oc, __float_as_int(r.lw), __float_as_int((1.0f - r.lh) * aw), __float_as_int(r.lh * aw));
+          } else {
+            s_cw[pt] = r.cw;
+            s_oc[pt] = r.oc;
+          }
         };
         int pt = sub;
         if constexpr (EARLY) {   // the loads of these iterations were issued before the level table's barrier
@@ -586,19 +638,45 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
         const int np = (PT > 0) ? PT : P;
 #pragma unroll
         for (int p = 0; p < np; ++p, ++pt) {
-          const int oc = s_oc[pt];
-          const float4 cw = s_cw[pt];
+          int oc;
+          float4 cw;
+          if constexpr (REC16) {
+            const int4 r = s_rec[pt];
+            oc = r.x;
+            const float lw = __int_as_float(r.y), wy0 = __int_as_float(r.z), wy1 = __int_as_float(r.w);
+            const float hw = 1.0f - lw;
+            cw = make_float4(wy0 * hw, wy0 * lw, wy1 * hw, wy1 * lw);
+          } else {
+            oc = s_oc[pt];
+            cw = s_cw[pt];
+          }
+          // A corner whose validity bit is clear is neither loaded nor added (its offset may lie outside the map).
+          // Loads first, then the FMAs: both compile to predicated instructions (R2P + @P LDG.E.128 / @P FFMA), no
+          // branches, and the loads of the next point are scheduled under the FMAs of this one.
           const int o00 = oc & ~15;
-          const int o01 = o00 + ((oc & 1) ? HD : 0);
-          const int dy = (oc & 2) ? dyl : 0;
-          const Vec<CPL> v00 = ldv<CPL>(vimg + o00);
-          const Vec<CPL> v01 = ldv<CPL>(vimg + o01);
-          const Vec<CPL> v10 = ldv<CPL>(vimg + (o00 + dy));
-          const Vec<CPL> v11 = ldv<CPL>(vimg + (o01 + dy));
-          fmav(acc, cw.x, v00);
-          fmav(acc, cw.y, v01);
-          fmav(acc, cw.z, v10);
-          fmav(acc, cw.w, v11);
+          if constexpr (sizeof(VT) == 4) {
+            Raw<CPL, VT> v0, v1, v2, v3;
+            if (oc & 1) v0 = ldraw<CPL>(vimg + o00);
+            if (oc & 2) v1 = ldraw<CPL>(vimg + (o00 + HD));
+            if (oc & 4) v2 = ldraw<CPL>(vimg + (o00 + dyl));
+            if (oc & 8) v3 = ldraw<CPL>(vimg + (o00 + dyl + HD));
+            if (oc & 1) fmav(acc, cw.x, unpack(v0));
+            if (oc & 2) fmav(acc, cw.y, unpack(v1));
+            if (oc & 4) fmav(acc, cw.z, unpack(v2));
+            if (oc & 8) fmav(acc, cw.w, unpack(v3));
+          } else {
+            // bf16: unpack + FMA of 8 channels is too long a body for the compiler to predicate (it branches, and the
+            // rows of a warp diverge), so the packed bits start as zeros and only the load is predicated
+            Raw<CPL, VT> v0 = Raw<CPL, VT>(), v1 = Raw<CPL, VT>(), v2 = Raw<CPL, VT>(), v3 = Raw<CPL, VT>();
+            if (oc & 1) v0 = ldraw<CPL>(vimg + o00);
+            if (oc & 2) v1 = ldraw<CPL>(vimg + (o00 + HD));
+            if (oc & 4) v2 = ldraw<CPL>(vimg + (o00 + dyl));
+            if (oc & 8) v3 = ldraw<CPL>(vimg + (o00 + dyl + HD));
+            fmav(acc, cw.x, unpack(v0));
+            fmav(acc, cw.y, unpack(v1));
+            fmav(acc, cw.z, unpack(v2));
+            fmav(acc, cw.w, unpack(v3));
+          }
         }
       }
       stv<CPL>(out + cur.row * D + sub * CPL, acc);
@@ -819,7 +897,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
       // rows that do not exist get all-zero records
       auto build = [&](int pt, float2 xy, float aw) {
         float4 cw = zero;
-        int4 fin = make_int4(0, __float_as_int(-1.0f), 0, 0);
+        int4 fin = make_int4(0, 0, 0, 0);      // no validity bits: nothing is loaded, scattered or written
         if (cur.live) {
           const int l = level_of<PT>(pt, P);
           if constexpr (FUSED) {
@@ -829,10 +907,10 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           PointRec r;
           if constexpr (DCN) {
             const float2 px = dcn_location(xy, pt, (int)((cur.row / H) % Q), fused);
-            r = record_from_cell(locate_pixel(px.x, px.y, tab->H[0], tab->W[0]), aw, tab->H[0], tab->W[0], 0, H, cur.h, D);
+            r = record_from_cell(locate_pixel(px.x, px.y, tab->H[0], tab->W[0]), aw, tab->W[0], 0, H, cur.h, D);
           } else if constexpr (EMIT) {
             const Cell<float> c = locate<float>(xy.x, xy.y, tab->H[l], tab->W[l]);
-            r = record_from_cell(c, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
+            r = record_from_cell(c, aw, tab->W[l], tab->start[l], H, cur.h, D);
             if (c.valid != 0u) {   // same bin index as det_bin_kernel (msda_det.cuh): cells of the extended grid
               const int bin = (cur.b * H + cur.h) * tab->cells_per_bh + tab->cell_begin[l] +
                               (c.y0 + 1) * (tab->W[l] + 1) + (c.x0 + 1);
@@ -900,21 +978,22 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           const float4 cw = s_cw[pt];
           const int l = level_of<PT>(pt, P);
           const int o00 = oc & ~15;
-          const int o01 = o00 + ((oc & 1) ? HD : 0);
-          const int dy = (oc & 2) ? tab->W[l] * HD : 0;
-          const int o10 = o00 + dy, o11 = o01 + dy;
+          const int o01 = o00 + HD;
+          const int o10 = o00 + tab->W[l] * HD, o11 = o10 + HD;
+          // a corner whose validity bit is clear is not loaded (its offset may lie outside the map); its dot stays 0
+          float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
 #ifdef MSDA_EXP_NO_GATHER   // experiment builds only (tools/ablate.sh): what does the scatter cost alone?
-          const Vec<CPL> v00 = go, v01 = go, v10 = go, v11 = go;
+          d0 = d1 = d2 = d3 = dotv(go, go);
 #else
-          const Vec<CPL> v00 = ldv<CPL>(vimg + o00);
-          const Vec<CPL> v01 = ldv<CPL>(vimg + o01);
-          const Vec<CPL> v10 = ldv<CPL>(vimg + o10);
-          const Vec<CPL> v11 = ldv<CPL>(vimg + o11);
+          if (oc & 1) d0 = dotv(go, ldv<CPL>(vimg + o00));
+          if (oc & 2) d1 = dotv(go, ldv<CPL>(vimg + o01));
+          if (oc & 4) d2 = dotv(go, ldv<CPL>(vimg + o10));
+          if (oc & 8) d3 = dotv(go, ldv<CPL>(vimg + o11));
 #endif
-          d[4 * j + 0] = dotv(go, v00);
-          d[4 * j + 1] = dotv(go, v01);
-          d[4 * j + 2] = dotv(go, v10);
-          d[4 * j + 3] = dotv(go, v11);
+          d[4 * j + 0] = d0;
+          d[4 * j + 1] = d1;
+          d[4 * j + 2] = d2;
+          d[4 * j + 3] = d3;
 #ifdef MSDA_EXP_NO_RED      // experiment builds only: what does the gather cost alone?
           if (cw.x == 12345.678f) scatterv<CPL, D / 2>(reinterpret_cast<float*>(gimg) + o00, cw.x, go);
 #else
@@ -942,16 +1021,9 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         const int4 r = s_fin[mine];
         const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
         float g_aw = 0.0f, g_x = 0.0f, g_y = 0.0f;      // a gated point's grads stay 0 (cuh:369)
-        if (lw >= 0.0f) {
-          const bool x0v = (r.x & 4) != 0, y0v = (r.x & 8) != 0;
-          const bool x1v = (r.x & 1) != 0 || !x0v, y1v = (r.x & 2) != 0 || !y0v;
-          unsigned msk = 0;   // FUSED with a padding mask: corners whose value row reads as zeros
-          if constexpr (FUSED) {
-            if (fused.value_mask) msk = masked_corners(s_cw[mine]);
-          }
-          // d[k] = <grad_out, v_k>; padded (and masked) corners contribute 0 (cuh:119-158)
-          const float d0 = (x0v && y0v && !(msk & 1u)) ? d[0] : 0.0f, d1 = (x1v && y0v && !(msk & 2u)) ? d[1] : 0.0f;
-          const float d2 = (x0v && y1v && !(msk & 4u)) ? d[2] : 0.0f, d3 = (x1v && y1v && !(msk & 8u)) ? d[3] : 0.0f;
+        if (r.x & 15) {
+          // d[k] = <grad_out, v_k>; padded (and masked) corners were not loaded and contribute 0 (cuh:119-158)
+          const float d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];
           const float hh = 1.0f - lh, hw = 1.0f - lw;
           const int l = level_of<PT>(mine, P);
           g_aw = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;

@@ -137,7 +137,7 @@ msda_bwd_fold_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
         if constexpr (FUSED) sm_sum = row_softmax<LANES, 4>(wp, reinterpret_cast<float*>(s_fin) + 3, NP, sub);
         for (int pt = sub; pt < NP; pt += LANES) {
           float4 cw = zero;
-          int4 fin = make_int4(0, __float_as_int(-1.0f), 0, 0);
+          int4 fin = make_int4(0, 0, 0, 0);
           if (live) {
             float2 xy = __ldg(lp + pt);
             float aw = 0.0f;
@@ -155,13 +155,12 @@ msda_bwd_fold_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             cw = r.cw;
             fin = make_int4(r.oc, __float_as_int(r.lw), __float_as_int(r.lh), __float_as_int(aw));
             // file the non-zero corners under their destination pixel
-            const int dx = r.oc & 1, dy = (r.oc & 2) ? tab->W[l] : 0;
             const int ebase = (rin * NP + pt) * 4;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float c = (k == 0) ? cw.x : ((k == 1) ? cw.y : ((k == 2) ? cw.z : cw.w));
-              if (c == 0.0f) continue;   // padded, gated or masked (-0.0f) corner
-              const int pix = r.pix + ((k & 1) ? dx : 0) + ((k & 2) ? dy : 0);
+              if (c == 0.0f) continue;   // padded, gated or masked corner (or a weight that happens to be 0)
+              const int pix = r.pix + (k & 1) + ((k & 2) ? tab->W[l] : 0);
               unsigned slot = ((unsigned)pix * 2654435761u) >> (32 - kFoldLogSlots);
               bool filed = false;
 #pragma unroll 1
@@ -206,16 +205,16 @@ msda_bwd_fold_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             const int oc = s_fin[pt].x;
             const int l = level_of<PT>(pt, P);
             const int o00 = oc & ~15;
-            const int o01 = o00 + ((oc & 1) ? HD : 0);
-            const int dy = (oc & 2) ? tab->W[l] * HD : 0;
-            const Vec<4> v00 = ldv<4>(vimg + o00);
-            const Vec<4> v01 = ldv<4>(vimg + o01);
-            const Vec<4> v10 = ldv<4>(vimg + (o00 + dy));
-            const Vec<4> v11 = ldv<4>(vimg + (o01 + dy));
-            d[4 * j + 0] = dotv(go, v00);
-            d[4 * j + 1] = dotv(go, v01);
-            d[4 * j + 2] = dotv(go, v10);
-            d[4 * j + 3] = dotv(go, v11);
+            const int o10 = o00 + tab->W[l] * HD;
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            if (oc & 1) d0 = dotv(go, ldv<4>(vimg + o00));
+            if (oc & 2) d1 = dotv(go, ldv<4>(vimg + (o00 + HD)));
+            if (oc & 4) d2 = dotv(go, ldv<4>(vimg + o10));
+            if (oc & 8) d3 = dotv(go, ldv<4>(vimg + (o10 + HD)));
+            d[4 * j + 0] = d0;
+            d[4 * j + 1] = d1;
+            d[4 * j + 2] = d2;
+            d[4 * j + 3] = d3;
           } else {
             d[4 * j + 0] = 0.f; d[4 * j + 1] = 0.f; d[4 * j + 2] = 0.f; d[4 * j + 3] = 0.f;
           }
@@ -227,15 +226,8 @@ msda_bwd_fold_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           const float lw = __int_as_float(r.y), lh = __int_as_float(r.z), aw = __int_as_float(r.w);
           float g_aw = 0.0f, g_x = 0.0f, g_y = 0.0f;
           const int l = level_of<PT>(mine, P);
-          if (lw >= 0.0f) {
-            const bool x0v = (r.x & 4) != 0, y0v = (r.x & 8) != 0;
-            const bool x1v = (r.x & 1) != 0 || !x0v, y1v = (r.x & 2) != 0 || !y0v;
-            unsigned msk = 0;
-            if constexpr (FUSED) {
-              if (fused.value_mask) msk = masked_corners(s_cw[mine]);
-            }
-            const float d0 = (x0v && y0v && !(msk & 1u)) ? d[0] : 0.0f, d1 = (x1v && y0v && !(msk & 2u)) ? d[1] : 0.0f;
-            const float d2 = (x0v && y1v && !(msk & 4u)) ? d[2] : 0.0f, d3 = (x1v && y1v && !(msk & 8u)) ? d[3] : 0.0f;
+          if (r.x & 15) {
+            const float d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];   // corners without a validity bit were not loaded
             const float hh = 1.0f - lh, hw = 1.0f - lw;
             g_aw = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;
             g_x = (hh * (d1 - d0) + lh * (d3 - d2)) * aw;

@@ -241,6 +241,41 @@ def test_fused_function_folds_the_padding_mask(ref_dim, D, L, P, dtype):
     assert torch.equal(out_c, out_a)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_mask_discards_non_finite_values(dtype):
+    """masked_fill(key_padding_mask, 0) DISCARDS whatever value_proj produced under the mask (py:291-292) -- an
+    overflowed bf16 activation, say.  The fused kernels never load a masked corner, so NaN / Inf there cannot reach
+    the output or any gradient: bit-identical to the same call with finite values under the mask."""
+    from ir_ads_b200.functional import MSDeformAttnFusedFunction
+    from ir_ads_b200.workloads import level_tensors
+
+    torch.manual_seed(5)
+    levels = [(11, 17), (6, 9), (3, 5)]
+    shapes, lsi = level_tensors(levels, DEV)
+    S = sum(h * w for h, w in levels)
+    B, Q, H, D, L, P = 2, 53, 4, 32, 3, 4
+    value = torch.randn(B, S, H, D, device=DEV).to(dtype)
+    offsets = torch.randn(B, Q, H, L, P, 2, device=DEV) * 3.0
+    logits = torch.randn(B, Q, H, L * P, device=DEV)
+    ref = torch.rand(B, Q, L, 2, device=DEV) * 1.2 - 0.1
+    go = torch.randn(B, Q, H * D, device=DEV).to(dtype)
+    mask = torch.rand(B, S, device=DEV) < 0.4
+    poisoned = value.clone()
+    poisoned[mask] = float("nan")
+    poisoned[mask & (torch.rand(B, S, device=DEV) < 0.5)] = float("inf")
+    res = []
+    for val in (poisoned, value):
+        leaves = [t.clone().requires_grad_(True) for t in (val, offsets, logits)]
+        out = MSDeformAttnFusedFunction.apply(leaves[0], shapes, lsi, leaves[1], leaves[2], ref, mask)
+        out.backward(go)
+        res.append([out.detach()] + [t.grad for t in leaves])
+    assert all(torch.isfinite(t).all() for t in res[0])
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
+    assert res[0][1][mask].abs().max() == 0
+    gv_a, gv_b = res[0][1].float(), res[1][1].float()          # atomics: equal up to summation order
+    assert (gv_a - gv_b).abs().max() <= (1e-5 if dtype == torch.float32 else 1e-2) * gv_b.abs().max() + 1e-6
+
+
 @pytest.mark.parametrize("seed", list(range(8)))
 def test_fused_function_random_shapes_against_composition(seed):
     """Seeded fuzz of the fused path (softmax + location affine + optional padding mask inside the kernels) against

@@ -608,6 +608,41 @@ def test_nan_and_inf_locations_are_skipped():
     assert torch.isfinite(got).all() and torch.equal(got, want) and not torch.equal(got, base)
 
 
+def test_non_finite_values_outside_a_points_footprint_do_not_leak():
+    """A corner that is zero padding for a point is never LOADED (the reference's per-corner bounds checks, cuh:56-80,
+    skip it too), so a NaN / Inf in a pixel no point actually samples -- here the first and last pixel of every level,
+    with a third of the points gated out altogether -- leaves the output and every gradient finite and bit-identical
+    to the same problem with zeros in those pixels.  (Round 1 clamped padded corners onto the border pixel with weight
+    0 and multiplied: 0 * NaN.)"""
+    ir, _, _, workloads, *_ = _mods()
+    levels = [(14, 20), (9, 12), (5, 7)]
+    for dtype in (torch.float32, torch.bfloat16):
+        v, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 60, 4, 32, 4, "decoder", "test", 5, DEV)
+        g = torch.Generator(device=DEV).manual_seed(3)
+        loc = torch.rand(loc.shape, device=DEV, generator=g) * 0.45 + 0.3          # well inside every level
+        gate = torch.rand(loc.shape[:-1], device=DEV, generator=g) < 0.33
+        far = torch.where(torch.rand(loc.shape, device=DEV, generator=g) < 0.5, -0.7, 1.6)
+        loc = torch.where(gate[..., None], far, loc)
+        v = v.to(dtype)
+        poisoned = v.clone()
+        start = 0
+        for h, wd in levels:
+            poisoned[:, start] = float("nan")
+            poisoned[:, start + h * wd - 1] = float("inf")
+            start += h * wd
+        go = torch.randn(2, 60, 4 * 32, device=DEV, generator=g).to(dtype)
+        res = []
+        for val in (poisoned, v):
+            vv, lo, ww = val.clone().requires_grad_(True), loc.clone().requires_grad_(True), w.clone().requires_grad_(True)
+            out = ir.MultiScaleDeformableAttnFunction.apply(vv, shapes, lsi, lo, ww, 64)
+            out.backward(go)
+            res.append((out.detach(), vv.grad, lo.grad, ww.grad))
+        for a, b in zip(res[0][:1] + res[0][2:], res[1][:1] + res[1][2:]):
+            assert torch.isfinite(a).all() and torch.equal(a, b)
+        assert torch.isfinite(res[0][1]).all()                 # nothing is scattered from a poisoned row either
+        assert (res[0][1].float() - res[1][1].float()).abs().max() <= 1e-2 * res[1][1].float().abs().max()
+
+
 def test_non_contiguous_grad_output_and_errors():
     ir, _lib, _, workloads, *_ = _mods()
     v, shapes, lsi, loc, w = workloads.make_inputs([(5, 6), (2, 3)], 2, 4, 2, 32, 2, "decoder", "test", 3, DEV)

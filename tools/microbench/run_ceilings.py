@@ -63,6 +63,11 @@ def main():
                         "gives the same rate)",
         "raw": {"gather_v8": g.strip().splitlines(), "red_vs_tma": r.strip().splitlines()},
     }
+    try:                                   # hand-entered ncu counters of the kernels (not measured here) are kept
+        with open(out_path) as f:
+            res["ncu_counters_cfg2"] = json.load(f)["ncu_counters_cfg2"]
+    except (OSError, KeyError, ValueError):
+        pass
     with open(out_path, "w") as f:
         json.dump(res, f, indent=1)
     print(json.dumps({k: v for k, v in res.items() if k not in ("raw", "_comment")}, indent=1))
