@@ -17,6 +17,15 @@ from ir_ads_b200 import functional  # noqa: E402
 from ir_ads_b200.workloads import WORKLOADS, make_workload_inputs  # noqa: E402
 
 
+def hbm_peak_gbs():
+    """The roofline denominator bench.py uses: MEASURED_PEAKS.json hbm_gbs, else B200_PROFILING.md's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
 def time_variant(wl, dist, flags, iters, sets=3, dev="cuda:0", deterministic=False):
     data = []
     odt = torch.bfloat16 if wl.value_dtype == "bf16" else torch.float32
@@ -42,10 +51,11 @@ def time_variant(wl, dist, flags, iters, sets=3, dev="cuda:0", deterministic=Fal
     functional.set_deterministic(False)
     f, b = statistics.median(tf), statistics.median(tb)
     fb, bb = wl.algorithmic_bytes()
+    peak = hbm_peak_gbs()
     return {"workload": wl.name, "dist": dist, "flags": flags, "det": deterministic, "fwd_ms": round(f, 4),
             "bwd_ms": round(b, 4), "gpts_s": round(wl.points / (f + b) / 1e6, 3),
-            "fwd_frac_hbm": round(fb / f / 1e6 / 6439.8, 4), "bwd_frac_hbm": round(bb / b / 1e6 / 6439.8, 4),
-            "fb_frac_hbm": round((fb + bb) / (f + b) / 1e6 / 6439.8, 4)}
+            "fwd_frac_hbm": round(fb / f / 1e6 / peak, 4), "bwd_frac_hbm": round(bb / b / 1e6 / peak, 4),
+            "fb_frac_hbm": round((fb + bb) / (f + b) / 1e6 / peak, 4)}
 
 
 def main():
