@@ -35,6 +35,24 @@
 
 #include "msda_coords.cuh"
 
+// -DMSDA_DEBUG_BOUNDS (variant builds only, tools/build_variant.sh): every corner offset that is about to be
+// dereferenced -- gather, scatter, padding-mask byte -- is checked against the image; a violation prints and traps.
+// The records hold UNCLAMPED offsets whose validity bits alone keep the loops inside the map, and compute-sanitizer
+// is not available on the GPU pool, so this is the memcheck of the parity suite (tools/gpu_r02n.sh).
+#ifdef MSDA_DEBUG_BOUNDS
+#include <cstdio>
+#define MSDA_CHECK_OFFSET(off, limit, what)                                                                  \
+  do {                                                                                                       \
+    if ((unsigned)(off) >= (unsigned)(limit)) {                                                              \
+      printf("msda bounds: %s offset %d outside [0, %d) (block %d thread %d)\n", what, (int)(off), (int)(limit), \
+             (int)blockIdx.x, (int)threadIdx.x);                                                             \
+      __trap();                                                                                              \
+    }                                                                                                        \
+  } while (0)
+#else
+#define MSDA_CHECK_OFFSET(off, limit, what) ((void)0)
+#endif
+
 namespace msda {
 
 constexpr int kFastMaxLevels = 16;
@@ -458,8 +476,16 @@ __device__ __forceinline__ float2 fused_location(const float2 off, const float* 
 // nothing into it (grad_value of a masked pixel stays 0, which is masked_fill's own backward) and drops its value
 // from grad_sampling_loc / grad_attn_weight -- whereas a corner whose weight merely happens to be 0 (lw == 0, say)
 // keeps its bit and still enters the location gradient.  Only the mask bytes of in-map corners are read.
-__device__ __forceinline__ void apply_value_mask(PointRec& r, const unsigned char* mask_img, int Wl) {
+__device__ __forceinline__ void apply_value_mask(PointRec& r, const unsigned char* mask_img, int Wl, int S) {
   const int v = r.oc & 15;
+#ifdef MSDA_DEBUG_BOUNDS
+  if (v & 1) MSDA_CHECK_OFFSET(r.pix, S, "mask k0");
+  if (v & 2) MSDA_CHECK_OFFSET(r.pix + 1, S, "mask k1");
+  if (v & 4) MSDA_CHECK_OFFSET(r.pix + Wl, S, "mask k2");
+  if (v & 8) MSDA_CHECK_OFFSET(r.pix + Wl + 1, S, "mask k3");
+#else
+  (void)S;
+#endif
   const bool k0 = (v & 1) && __ldg(mask_img + r.pix) == 0, k1 = (v & 2) && __ldg(mask_img + r.pix + 1) == 0;
   const bool k2 = (v & 4) && __ldg(mask_img + r.pix + Wl) == 0, k3 = (v & 8) && __ldg(mask_img + r.pix + Wl + 1) == 0;
   r.cw.x = k0 ? r.cw.x : 0.0f;
@@ -607,7 +633,7 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
             r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
           }
           if constexpr (FUSED) {
-            if (fused.value_mask) apply_value_mask(r, fused.value_mask + (int64_t)cur.b * S, tab->W[l]);
+            if (fused.value_mask) apply_value_mask(r, fused.value_mask + (int64_t)cur.b * S, tab->W[l], S);
           }
           if constexpr (REC16) {
             s_rec[pt] = make_int4(r.oc, __float_as_int(r.lw), __float_as_int((1.0f - r.lh) * aw), __float_as_int(r.lh * aw));
@@ -654,6 +680,12 @@ msda_fwd_fast_kernel(const VT* __restrict__ value, const int64_t* __restrict__ s
           // Loads first, then the FMAs: both compile to predicated instructions (R2P + @P LDG.E.128 / @P FFMA), no
           // branches, and the loads of the next point are scheduled under the FMAs of this one.
           const int o00 = oc & ~15;
+#ifdef MSDA_DEBUG_BOUNDS
+          if (oc & 1) MSDA_CHECK_OFFSET(o00, S * HD, "fwd k0");
+          if (oc & 2) MSDA_CHECK_OFFSET(o00 + HD, S * HD, "fwd k1");
+          if (oc & 4) MSDA_CHECK_OFFSET(o00 + dyl, S * HD, "fwd k2");
+          if (oc & 8) MSDA_CHECK_OFFSET(o00 + dyl + HD, S * HD, "fwd k3");
+#endif
           if constexpr (sizeof(VT) == 4) {
             Raw<CPL, VT> v0, v1, v2, v3;
             if (oc & 1) v0 = ldraw<CPL>(vimg + o00);
@@ -921,7 +953,7 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, cur.h, D);
           }
           if constexpr (FUSED) {
-            if (fused.value_mask) apply_value_mask(r, fused.value_mask + (int64_t)cur.b * S, tab->W[l]);
+            if (fused.value_mask) apply_value_mask(r, fused.value_mask + (int64_t)cur.b * S, tab->W[l], S);
           }
           cw = r.cw;
           fin = make_int4(r.oc, __float_as_int(r.lw), __float_as_int(r.lh), __float_as_int(aw));
@@ -982,6 +1014,12 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
           const int o10 = o00 + tab->W[l] * HD, o11 = o10 + HD;
           // a corner whose validity bit is clear is not loaded (its offset may lie outside the map); its dot stays 0
           float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+#ifdef MSDA_DEBUG_BOUNDS
+          if ((oc & 1) || cw.x != 0.0f) MSDA_CHECK_OFFSET(o00, S * HD, "bwd k0");
+          if ((oc & 2) || cw.y != 0.0f) MSDA_CHECK_OFFSET(o01, S * HD, "bwd k1");
+          if ((oc & 4) || cw.z != 0.0f) MSDA_CHECK_OFFSET(o10, S * HD, "bwd k2");
+          if ((oc & 8) || cw.w != 0.0f) MSDA_CHECK_OFFSET(o11, S * HD, "bwd k3");
+#endif
 #ifdef MSDA_EXP_NO_GATHER   // experiment builds only (tools/ablate.sh): what does the scatter cost alone?
           d0 = d1 = d2 = d3 = dotv(go, go);
 #else

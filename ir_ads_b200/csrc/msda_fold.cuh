@@ -150,7 +150,7 @@ msda_bwd_fold_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             }
             PointRec r = make_record(xy.x, xy.y, aw, tab->H[l], tab->W[l], tab->start[l], H, h, D);
             if constexpr (FUSED) {
-              if (fused.value_mask) apply_value_mask(r, fused.value_mask + (int64_t)b * S, tab->W[l]);
+              if (fused.value_mask) apply_value_mask(r, fused.value_mask + (int64_t)b * S, tab->W[l], S);
             }
             cw = r.cw;
             fin = make_int4(r.oc, __float_as_int(r.lw), __float_as_int(r.lh), __float_as_int(aw));
