@@ -36,6 +36,10 @@
  *   grad_value         [B, S, H, D]        dtype        (zero-filled by the library)
  *   grad_sampling_loc, grad_attn_weight    shaped/typed like sampling_loc / attn_weight
  *                                          (fully written by the library, no pre-zeroing needed)
+ * Every tensor pointer (workspaces included) must be 16-byte aligned: rows are read and written with 128-bit
+ * accesses.  A torch / cudaMalloc allocation is; a view with an odd storage offset may not be -- such a call returns
+ * MSDA_ERR_INVALID_ARGUMENT (the Python wrappers re-align by copying).  The reference's scalar kernels had no such
+ * requirement.
  *
  * Thread safety: re-entrant, no global mutable state except a launch counter and a
  * thread-local last-error string; no library-owned streams, events or locks.  Work is enqueued on `stream` of the device that owns `value`

@@ -38,6 +38,14 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+int check_alignment(std::initializer_list<NamedPtr> ptrs) {
+  for (const NamedPtr& p : ptrs)
+    if (p.ptr && (reinterpret_cast<uintptr_t>(p.ptr) & 15u) != 0)
+      return fail(MSDA_ERR_INVALID_ARGUMENT, "%s (%p) is not 16-byte aligned: the kernels use 128-bit accesses", p.name,
+                  p.ptr);
+  return MSDA_OK;
+}
+
 bool fast_ok(const Dims& d, int dtype, unsigned flags) {
   if (flags & MSDA_FLAG_FORCE_GENERIC) return false;
   if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
@@ -284,6 +292,9 @@ int msda_forward(void* stream, const void* value, const int64_t* spatial_shapes,
   if (int s = check_dims(d, dtype)) return s;
   if (d.rows() * d.D == 0) return MSDA_OK;  // nothing to write (the reference would launch a 0-block grid, cuh:942)
   if (!output) return fail(MSDA_ERR_INVALID_ARGUMENT, "output is null");
+  if (int s = check_alignment({{"value", value}, {"sampling_loc", sampling_loc}, {"attn_weight", attn_weight},
+                               {"output", output}}))
+    return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d.n_points() == 0 || d.S == 0) {  // no samples: the sum over an empty set
     DeviceGuard g;
@@ -334,6 +345,11 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
   const size_t es = elem_size(dtype);
   const size_t ls = dtype == MSDA_F64 ? 8 : 4;
   if (d.n_value() == 0 && d.n_points() == 0) return MSDA_OK;
+  if (int s = check_alignment({{"grad_output", grad_output}, {"value", value}, {"sampling_loc", sampling_loc},
+                               {"attn_weight", attn_weight}, {"grad_value", grad_value},
+                               {"grad_sampling_loc", grad_sampling_loc}, {"grad_attn_weight", grad_attn_weight},
+                               {"workspace", workspace}}))
+    return s;
   if ((flags & MSDA_FLAG_NO_GRAD_VALUE) && d.n_value() != 0 && d.n_points() != 0 && fast_ok(d, dtype, flags)) {
     // grad_value not wanted: the regular kernel with the scatter compiled out (no zero-fill, no workspace)
     if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight ||
@@ -538,6 +554,9 @@ int msda_fused_forward(void* stream, const void* value, const int64_t* spatial_s
   if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !reference_points ||
       !output)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  if (int s = check_alignment({{"value", value}, {"sampling_offsets", sampling_offsets}, {"attn_logits", attn_logits},
+                               {"reference_points", reference_points}, {"output", output}}))
+    return s;
   DeviceGuard guard;
   MSDA_CUDA(guard.enter(value));
   msda::FusedArgs fa{};
@@ -566,6 +585,11 @@ int msda_fused_backward(void* stream, const void* grad_output, const void* value
   if (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits ||
       !reference_points || !grad_value || !grad_offsets || !grad_logits)
     return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  if (int s = check_alignment({{"grad_output", grad_output}, {"value", value}, {"sampling_offsets", sampling_offsets},
+                               {"attn_logits", attn_logits}, {"reference_points", reference_points},
+                               {"grad_value", grad_value}, {"grad_offsets", grad_offsets}, {"grad_logits", grad_logits},
+                               {"workspace", workspace}}))
+    return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DeviceGuard guard;
   MSDA_CUDA(guard.enter(value));
@@ -638,6 +662,7 @@ int msda_dcnv3_forward(void* stream, const void* input, const float* offset, con
     return s;
   if (d.rows() * d.D == 0) return MSDA_OK;
   if (!output) return fail(MSDA_ERR_INVALID_ARGUMENT, "output is null");
+  if (int s = check_alignment({{"input", input}, {"offset", offset}, {"mask", mask}, {"output", output}})) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DeviceGuard guard;
   MSDA_CUDA(guard.enter(output));
@@ -666,6 +691,10 @@ int msda_dcnv3_backward(void* stream, const void* grad_output, const void* input
   if (d.n_value() == 0 && d.n_points() == 0) return MSDA_OK;
   const void* anchor = d.n_value() ? grad_input : (const void*)grad_mask;
   if (!anchor) return fail(MSDA_ERR_INVALID_ARGUMENT, "gradient output pointer is null");
+  if (int s = check_alignment({{"grad_output", grad_output}, {"input", input}, {"offset", offset}, {"mask", mask},
+                               {"grad_input", grad_input}, {"grad_offset", grad_offset}, {"grad_mask", grad_mask},
+                               {"workspace", workspace}}))
+    return s;
   DeviceGuard guard;
   MSDA_CUDA(guard.enter(anchor));
   const size_t need = dtype == MSDA_BF16 ? (size_t)d.n_value() * sizeof(float) : 0;

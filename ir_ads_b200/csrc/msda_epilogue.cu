@@ -197,6 +197,7 @@ int msda_add_layernorm_forward(void* stream, const void* a, const void* b, const
   if (int s = check_ln(rows, channels, dtype)) return s;
   if (rows == 0 || channels == 0) return MSDA_OK;
   if (!a || !b || !gamma || !beta || !y || !mean || !rstd) return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  if (int s = check_alignment({{"a", a}, {"b", b}, {"gamma", gamma}, {"beta", beta}, {"y", y}})) return s;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = ln_grid(rows);
   const int nv = (channels + 127) / 128;
@@ -232,6 +233,9 @@ int msda_add_layernorm_backward(void* stream, const void* grad_y, const void* a,
     return MSDA_OK;
   }
   if (!grad_y || !a || !b || !gamma || !mean || !rstd || !grad_x) return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  if (int s = check_alignment({{"grad_y", grad_y}, {"a", a}, {"b", b}, {"gamma", gamma}, {"grad_x", grad_x},
+                               {"workspace", workspace}}))
+    return s;
   const size_t need = msda_add_layernorm_workspace_bytes(rows, channels);
   if (!workspace || workspace_bytes < need)
     return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, %zu given", need, workspace_bytes);

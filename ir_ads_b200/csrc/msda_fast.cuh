@@ -1085,12 +1085,12 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
             const float* r4 = rp + l * 4;
             g_off = make_float2(g_x * 0.5f * __ldg(r4 + 2) * fused.inv_P, g_y * 0.5f * __ldg(r4 + 3) * fused.inv_P);
           }
-          *reinterpret_cast<float2*>(glp + 2 * mine) = g_off;
-          s_fin[mine].y = __float_as_int(g_aw);   // this point's record is finished: park grad_aw there
+          // this point's record is finished: park the three gradients in it ({g_x, g_aw, g_y, aw}); the row writes
+          // them out in full lines below
+          s_fin[mine] = make_int4(__float_as_int(g_off.x), __float_as_int(g_aw), __float_as_int(g_off.y), r.w);
           sm_dot = fmaf(g_aw, aw, sm_dot);
         } else {
-          gwp[mine] = g_aw;
-          *reinterpret_cast<float2*>(glp + 2 * mine) = make_float2(g_x, g_y);
+          s_fin[mine] = make_int4(__float_as_int(g_x), __float_as_int(g_aw), __float_as_int(g_y), r.w);
         }
       }
     }
@@ -1098,11 +1098,29 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
       // softmax backward: grad_logit_i = aw_i * (grad_aw_i - sum_j grad_aw_j aw_j)
 #pragma unroll
       for (int k = LANES / 2; k > 0; k >>= 1) sm_dot += __shfl_xor_sync(0xffffffffu, sm_dot, k);
-      __syncwarp();
-      if (cur.live) {
+    }
+    __syncwarp();
+    // Write-out.  One lane per point storing 4 + 8 bytes as it finishes would send every 16-byte piece of grad_attn_weight
+    // and every 32-byte piece of grad_sampling_loc through the SM's crossbar port as a request of its own (header + one
+    // sector each: 16 port cycles per row at L*P = 16); the port is what binds this kernel.  Parked in the records and
+    // written by the row's lanes two points at a time, a row leaves as one 128-byte and one 64-byte request.
+    if (cur.live) {
+      auto gw_of = [&](const int4 r) {
+        const float g_aw = __int_as_float(r.y);
+        return FUSED ? __int_as_float(r.w) * (g_aw - sm_dot) : g_aw;
+      };
+      if ((NP & 1) == 0) {      // both row bases are then 16- / 8-byte aligned
+        for (int pt = 2 * sub; pt < NP; pt += 2 * LANES) {
+          const int4 a = s_fin[pt], b = s_fin[pt + 1];
+          *reinterpret_cast<float4*>(glp + 2 * pt) =
+              make_float4(__int_as_float(a.x), __int_as_float(a.z), __int_as_float(b.x), __int_as_float(b.z));
+          *reinterpret_cast<float2*>(gwp + pt) = make_float2(gw_of(a), gw_of(b));
+        }
+      } else {
         for (int pt = sub; pt < NP; pt += LANES) {
-          const int4 r = s_fin[pt];
-          gwp[pt] = __int_as_float(r.w) * (__int_as_float(r.y) - sm_dot);
+          const int4 a = s_fin[pt];
+          *reinterpret_cast<float2*>(glp + 2 * pt) = make_float2(__int_as_float(a.x), __int_as_float(a.z));
+          gwp[pt] = gw_of(a);
         }
       }
     }

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <initializer_list>
+
 #include "msda_fast.cuh"
 
 namespace msda_host {
@@ -35,6 +37,15 @@ void count_launch();
     cudaError_t e__ = (call);                                         \
     if (e__ != cudaSuccess) return ::msda_host::cuda_fail(e__, #call); \
   } while (0)
+
+// The kernels read and write rows with 128-bit accesses (LDG.E.128, REDG...F32x4, STG.E.128): every non-null tensor
+// pointer of a compute call must be 16-byte aligned (any torch allocation is; an odd storage offset is not).
+// Returns MSDA_OK or MSDA_ERR_INVALID_ARGUMENT naming the first offender.
+struct NamedPtr {
+  const char* name;
+  const void* ptr;
+};
+int check_alignment(std::initializer_list<NamedPtr> ptrs);
 
 // D in {16,32,64,128}, float / bf16 value, L <= 16, 1 <= L*P <= 64, 32-bit offsets inside one image
 bool fast_ok(const Dims& d, int dtype, unsigned flags);

@@ -24,7 +24,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from .functional import _DTYPE_TAG, _ptr, _require
+from .functional import _DTYPE_TAG, _aligned, _ptr, _require
 
 
 def _declare(handle):
@@ -60,6 +60,7 @@ def dcnv3_forward(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, p
                   group, group_channels, offset_scale, im2col_step=256) -> torch.Tensor:
     """``detrex._C.dcnv3_forward``: returns ``[N, H_out, W_out, group*group_channels]``."""
     N, H_in, W_in, H_out, W_out = _geometry(input, offset, mask, kernel_h, kernel_w, group, group_channels)
+    input, offset, mask = _aligned(input), _aligned(offset), _aligned(mask)
     out = torch.empty((N, H_out, W_out, group * group_channels), dtype=input.dtype, device=input.device)
     stream = torch.cuda.current_stream(input.device).cuda_stream
     status = _declare(_lib.lib()).msda_dcnv3_forward(
@@ -75,7 +76,8 @@ def dcnv3_backward(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, 
     """``detrex._C.dcnv3_backward``: ``[grad_input, grad_offset, grad_mask]``."""
     N, H_in, W_in, H_out, W_out = _geometry(input, offset, mask, kernel_h, kernel_w, group, group_channels)
     _require(grad_output.is_cuda and grad_output.dtype == input.dtype, "grad_output must match input's device / dtype")
-    grad_output = grad_output.contiguous()
+    grad_output = _aligned(grad_output.contiguous())
+    input, offset, mask = _aligned(input), _aligned(offset), _aligned(mask)
     grad_input = torch.empty_like(input)
     grad_offset = torch.empty_like(offset)
     grad_mask = torch.empty_like(mask)

@@ -14,7 +14,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from .functional import _DTYPE_TAG, _ptr, _require
+from .functional import _DTYPE_TAG, _aligned, _ptr, _require
 
 
 def add_layer_norm_supported(x: torch.Tensor) -> bool:
@@ -32,8 +32,8 @@ class AddLayerNormFunction(Function):
         _require(a.dtype in (torch.float32, torch.bfloat16), f"unsupported dtype {a.dtype} (float32, bfloat16)")
         C = a.shape[-1]
         _require(tuple(weight.shape) == (C,) and tuple(bias.shape) == (C,), "weight / bias must be [C]")
-        a, b = a.contiguous(), b.contiguous()
-        w32, b32 = weight.float().contiguous(), bias.float().contiguous()
+        a, b = _aligned(a.contiguous()), _aligned(b.contiguous())
+        w32, b32 = _aligned(weight.float().contiguous()), _aligned(bias.float().contiguous())
         rows = a.numel() // C if C else 0
         y = torch.empty_like(a)
         mean = torch.empty(rows, dtype=torch.float32, device=a.device)
@@ -53,7 +53,7 @@ class AddLayerNormFunction(Function):
         a, b, w32, mean, rstd = ctx.saved_tensors
         C = a.shape[-1]
         rows = a.numel() // C
-        grad_y = grad_y.contiguous()
+        grad_y = _aligned(grad_y.contiguous())
         _require(grad_y.dtype == a.dtype and grad_y.shape == a.shape, "grad_output must match the output")
         dx = torch.empty_like(a)
         dgamma = torch.empty(C, dtype=torch.float32, device=a.device)

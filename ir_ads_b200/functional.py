@@ -62,6 +62,15 @@ def _require(cond: bool, msg: str) -> None:
         raise RuntimeError(msg)
 
 
+def _aligned(t):
+    """The kernels use 128-bit accesses (include/msda.h): a contiguous tensor whose storage offset leaves it off a
+    16-byte boundary (a slice of a flat buffer, say) is copied into a fresh allocation.  Never the case for tensors
+    that own their storage; the reference's scalar kernels had no such requirement, so the wrappers hide it."""
+    if t is None or t.numel() == 0 or t.data_ptr() % 16 == 0:
+        return t
+    return t.clone(memory_format=torch.contiguous_format)
+
+
 def _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight):
     # mirrors the AT_ASSERTM block of ms_deform_attn_cuda.cu:29-39
     _require(value.is_cuda, "Not implemented on the CPU")  # ms_deform_attn.h:39
@@ -93,6 +102,7 @@ def ms_deform_attn_forward(value: torch.Tensor, spatial_shapes: torch.Tensor, le
                            sampling_loc: torch.Tensor, attn_weight: torch.Tensor, im2col_step: int = 64) -> torch.Tensor:
     """``detrex._C.ms_deform_attn_forward`` (vision.cpp:55): returns ``[B, Q, H*D]`` in value's dtype."""
     B, S, H, D, L, Q, P = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    value, sampling_loc, attn_weight = _aligned(value), _aligned(sampling_loc), _aligned(attn_weight)
     out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
     stream = torch.cuda.current_stream(value.device).cuda_stream
     status = _lib.lib().msda_forward(ctypes.c_void_p(stream), _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
@@ -118,7 +128,8 @@ def _backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weigh
     _require(grad_output.is_cuda and grad_output.device == value.device, "grad_output must be a CUDA tensor")
     _require(grad_output.dtype == value.dtype, "grad_output dtype must match value")
     _require(grad_output.numel() == B * Q * H * D, "grad_output must be [B, Q, H*D]")
-    grad_output = grad_output.contiguous()
+    grad_output = _aligned(grad_output.contiguous())
+    value, sampling_loc, attn_weight = _aligned(value), _aligned(sampling_loc), _aligned(attn_weight)
     grad_loc = torch.empty_like(sampling_loc)
     grad_w = torch.empty_like(attn_weight)
     flags = _flags(True)
@@ -268,6 +279,8 @@ class MSDeformAttnFusedFunction(Function):
                 key_padding_mask=None):
         (B, S, H, D, L, Q, P, ref_dim), mask = _check_fused_inputs(
             value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, key_padding_mask)
+        value, sampling_offsets, attn_logits, reference_points = (
+            _aligned(value), _aligned(sampling_offsets), _aligned(attn_logits), _aligned(reference_points))
         out = torch.empty((B, Q, H * D), dtype=value.dtype, device=value.device)
         stream = torch.cuda.current_stream(value.device).cuda_stream
         status = _lib.lib().msda_fused_forward(
@@ -289,7 +302,7 @@ class MSDeformAttnFusedFunction(Function):
         _require(grad_output.is_cuda and grad_output.device == value.device, "grad_output must be a CUDA tensor")
         _require(grad_output.dtype == value.dtype, "grad_output dtype must match value")
         _require(grad_output.numel() == B * Q * H * D, "grad_output must be [B, Q, H*D]")
-        grad_output = grad_output.contiguous()
+        grad_output = _aligned(grad_output.contiguous())
         flags = _flags(True)
         mask = ctx.value_mask
         need_ref = ctx.needs_input_grad[5]

@@ -643,6 +643,40 @@ def test_non_finite_values_outside_a_points_footprint_do_not_leak():
         assert (res[0][1].float() - res[1][1].float()).abs().max() <= 1e-2 * res[1][1].float().abs().max()
 
 
+def test_misaligned_tensors():
+    """Rows are read and written with 128-bit accesses, so the C ABI requires 16-byte aligned pointers (include/msda.h)
+    and says so instead of faulting; the Python wrappers copy a mis-aligned view (a slice of a flat buffer at an odd
+    element offset) into a fresh allocation, as the reference's scalar kernels needed no alignment at all."""
+    ir, _lib, functional, workloads, *_ = _mods()
+    v, shapes, lsi, loc, w = workloads.make_inputs([(6, 7), (3, 4)], 2, 9, 2, 32, 2, "decoder", "test", 1, DEV)
+    go = torch.randn(2, 9, 2 * 32, device=DEV)
+
+    def off_by_one(t):
+        flat = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+        view = flat[1:].view(t.shape)
+        view.copy_(t)
+        assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+        return view
+
+    want = ir.ms_deform_attn_forward(v, shapes, lsi, loc, w, 64)
+    got = ir.ms_deform_attn_forward(off_by_one(v), shapes, lsi, off_by_one(loc), off_by_one(w), 64)
+    assert torch.equal(got, want)
+    gw = ir.ms_deform_attn_backward(v, shapes, lsi, loc, w, go, 64)
+    gg = ir.ms_deform_attn_backward(off_by_one(v), shapes, lsi, off_by_one(loc), off_by_one(w), off_by_one(go), 64)
+    assert torch.equal(gg[1], gw[1]) and torch.equal(gg[2], gw[2])
+    assert (gg[0] - gw[0]).abs().max() <= 1e-5 * gw[0].abs().max()
+    # the C ABI itself refuses
+    bad = off_by_one(v)
+    out = torch.empty(2, 9, 64, device=DEV)
+    B, S, H, D = v.shape
+    status = _lib.lib().msda_forward(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
+                                     ctypes.c_void_p(bad.data_ptr()), ctypes.c_void_p(shapes.data_ptr()),
+                                     ctypes.c_void_p(lsi.data_ptr()), ctypes.c_void_p(loc.data_ptr()),
+                                     ctypes.c_void_p(w.data_ptr()), B, S, H, D, 2, 9, 2, ctypes.c_void_p(out.data_ptr()),
+                                     _lib.MSDA_F32, 0)
+    assert status != 0 and b"16-byte aligned" in _lib.lib().msda_last_error_message()
+
+
 def test_non_contiguous_grad_output_and_errors():
     ir, _lib, _, workloads, *_ = _mods()
     v, shapes, lsi, loc, w = workloads.make_inputs([(5, 6), (2, 3)], 2, 4, 2, 32, 2, "decoder", "test", 3, DEV)
