@@ -182,10 +182,11 @@ def make_workload_inputs(wl: Workload, dist="model", seed=0, device="cpu", batch
 def valid_corner_fraction(loc: torch.Tensor, levels) -> float:
     """Share of the 4 * N bilinear corners of `loc` [B,Q,H,L,P,2] that lie inside their level (the rest is zero padding
     or belongs to gated-out points, ms_deform_im2col_cuda.cuh:288, :56-80): the rows the kernels actually load / scatter.
-    Bench bookkeeping only (fp32 evaluation of loc * size - 0.5; a fraction, not a parity quantity)."""
-    wh = torch.as_tensor([[w, h] for h, w in levels], dtype=torch.float32, device=loc.device)
+    Bench bookkeeping only; evaluated in float64 like the oracle's exact cell (the kernels' compensated fp32 split picks
+    the same cell, a plain fp32 product does not at exact-integer coordinates)."""
+    wh = torch.as_tensor([[w, h] for h, w in levels], dtype=torch.float64, device=loc.device)
     size = wh[None, None, None, :, None, :]
-    c = loc.float() * size - 0.5
+    c = loc.double() * size - 0.5
     lo = torch.floor(c)
     gate = ((c > -1.0) & (c < size)).all(-1)
     n_axis = ((lo >= 0).to(torch.int32) + (lo + 1 <= size - 1).to(torch.int32))        # valid corners per axis: 0..2

@@ -141,3 +141,32 @@ def test_workload_inputs_are_seeded_and_shaped():
     value, shapes, lsi, loc, w = a
     assert value.shape == (2, 75, 4, 16) and loc.shape == (2, 75, 4, 2, 4, 2) and w.shape == (2, 75, 4, 2, 4)
     assert lsi.tolist() == [0, 60] and torch.allclose(w.sum((-1, -2)), torch.ones(2, 75, 4), atol=1e-5)
+
+
+def test_misaligned_views_are_copied_before_the_c_abi_sees_them():
+    """include/msda.h: every tensor pointer must be 16-byte aligned (128-bit accesses); the wrappers copy a view that is not."""
+    from ir_ads_b200.functional import _aligned
+    flat = torch.arange(65, dtype=torch.float32)
+    view = flat[1:]
+    assert view.data_ptr() % 16 != 0
+    fixed = _aligned(view)
+    assert fixed.data_ptr() % 16 == 0 and torch.equal(fixed, view) and fixed.data_ptr() != view.data_ptr()
+    ok = torch.zeros(64)
+    assert _aligned(ok) is ok and _aligned(None) is None
+    empty = flat[1:1]
+    assert _aligned(empty) is empty          # nothing to dereference
+
+
+def test_valid_corner_fraction_matches_the_oracle_bookkeeping():
+    """bench.py scales the on-chip ceilings by the share of corners that lie inside their level (the rows the kernels
+    load and scatter); that share is the oracle's count of in-map corners."""
+    import numpy as np
+    from oracle import msda_c
+    levels = [(9, 13), (5, 7), (3, 4)]
+    for dist in ("model", "test", "edge"):
+        value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 50, 4, 32, 4, "decoder", dist, 7)
+        B, S, H, D = value.shape
+        offs, _ = msda_c.bookkeeping(loc.numpy(), shapes.numpy(), lsi.numpy(), B, S, H, D, False)
+        want = float((offs >= 0).sum()) / offs.size
+        got = workloads.valid_corner_fraction(loc, levels)
+        assert abs(got - want) < 1e-12, (dist, got, want)
