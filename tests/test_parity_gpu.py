@@ -548,6 +548,30 @@ def test_random_problem_shapes_against_oracle(seed):
     assert_close(gl * m, rgl * m, at, 1e-6, "grad_loc " + what)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("D", [16, 32, 128])
+@pytest.mark.parametrize("dist", ["test", "edge"])
+def test_degenerate_pyramids_against_oracle(dist, D, dtype):
+    """One-pixel, one-row and one-column levels: almost every bilinear cell has padded corners, low corners at -1 and
+    unclamped offsets in front of / behind the level (the records' validity bits alone keep the loops inside the map)."""
+    _, _, _, workloads, msda_c, _ = _mods()
+    levels = [(1, 1), (1, 7), (5, 1), (2, 2)]
+    value, shapes, lsi, loc, wgt = workloads.make_inputs(levels, 2, 40, 2, D, 3, "decoder", dist, 21, value_dtype=dtype)
+    loc = (loc - 0.5) * 1.6 + 0.5                              # a good share outside [0, 1] on both sides
+    go = torch.randn(2, 40, 2 * D, generator=torch.Generator().manual_seed(2)).to(dtype)
+    a = [value.float().numpy(), shapes.numpy(), lsi.numpy(), loc.numpy(), wgt.numpy()]
+    ref_out = msda_c.forward(*a, np.float64)
+    rgv, rgl, rgw = msda_c.backward(go.float().numpy(), *a, np.float64)
+    m = smooth_mask(a[3], a[1], band=1e-4)
+    out, gv, gl, gw = run_cuda(value, shapes, lsi, loc, wgt, go, dtype)
+    vt = 1e-5 if dtype == torch.float32 else 1e-2
+    at = 1e-5 if dtype == torch.float32 else 1e-4
+    assert_close(out, ref_out, vt, 1e-6, "out")
+    assert_close(gv, rgv, vt, 1e-6, "grad_value")
+    assert_close(gw, rgw, at, 1e-6, "grad_w")
+    assert_close(gl * m, rgl * m, at, 1e-6, "grad_loc")
+
+
 def test_pytorch_named_entry_point(golden):
     """multi_scale_deformable_attn_pytorch(value, shapes, loc, w) -- the reference's other public function
     (multi_scale_deform_attn.py:96-136) -- runs on the kernels and matches the reference-made vectors."""
