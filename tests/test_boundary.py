@@ -170,3 +170,43 @@ def test_valid_corner_fraction_matches_the_oracle_bookkeeping():
         want = float((offs >= 0).sum()) / offs.size
         got = workloads.valid_corner_fraction(loc, levels)
         assert abs(got - want) < 1e-12, (dist, got, want)
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/msda.h must compile as C99 (no C++ in the signatures) and a plain C
+    program must link against libmsda_b200.so and get error codes back -- here without a GPU: calls that fail their
+    argument checks never reach the device."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "msda.h"
+int main(void) {
+  if (msda_abi_version() != MSDA_ABI_VERSION) return 1;
+  if (strcmp(msda_status_string(MSDA_OK), "MSDA_OK") != 0) return 2;
+  /* negative dimension: refused before anything touches the device */
+  int s = msda_forward(NULL, NULL, NULL, NULL, NULL, NULL, -1, 4, 2, 32, 1, 1, 1, NULL, MSDA_F32, 0u);
+  if (s != MSDA_ERR_INVALID_ARGUMENT) return 3;
+  if (strlen(msda_last_error_message()) == 0) return 4;
+  /* unknown dtype tag */
+  if (msda_forward(NULL, NULL, NULL, NULL, NULL, NULL, 1, 4, 2, 32, 1, 1, 1, NULL, 77, 0u) != MSDA_ERR_INVALID_ARGUMENT) return 5;
+  /* an empty problem is a no-op */
+  if (msda_forward(NULL, NULL, NULL, NULL, NULL, NULL, 0, 4, 2, 32, 1, 1, 1, NULL, MSDA_F32, 0u) != MSDA_OK) return 6;
+  if (msda_backward_workspace_bytes(2, 10, 2, 32, 1, 3, 2, MSDA_BF16, 0u) != (size_t)2 * 10 * 2 * 32 * 4) return 7;
+  printf("c abi ok\n");
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+           "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir,
+           "-Wl,-rpath,/usr/local/cuda/lib64", "-Wl,--allow-shlib-undefined"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and "c abi ok" in run.stdout, (run.returncode, run.stdout, run.stderr)
