@@ -10,7 +10,9 @@
 // Per row the L*P sampling locations and attention weights are turned ONCE into compact records
 // in shared memory (cell offset + corner validity + weights) by the row's own lanes -- the
 // coordinate arithmetic of msda_coords.cuh is done once per point, not once per channel -- and
-// then broadcast-read by all lanes of the row in the gather loop.
+// then broadcast-read by all lanes of the row in the gather loop.  Corner loads, their FMAs (forward)
+// and dot products (backward) are predicated on the record's validity bits: a padded, gated or masked
+// corner is never loaded (see PointRec).
 //
 // Row order (which rows a CTA works on; results never depend on it):
 //   LINEAR  rows in memory order (b, q, h): a CTA = THREADS/LANES consecutive rows.
@@ -25,7 +27,7 @@
 // Backward: per point each lane forms 4 partial dot products <grad_out, corner_k> over its 4
 // channels; partials of 4 points are transposed-and-reduced across the row's lanes with a
 // butterfly of shuffles (no shared memory, no barriers), after which one lane per point finishes
-// grad_attn_weight / grad_sampling_loc and stores them.  grad_value is scattered with 128-bit
+// grad_attn_weight / grad_sampling_loc; the row writes them out in full lines at its end.  grad_value is scattered with 128-bit
 // vector reductions (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4) -- 4x fewer atomic
 // instructions than the reference's scalar atomicAdd (cuh:125-152).
 #pragma once
