@@ -86,8 +86,10 @@ extern "C" {
  * the backward kernel itself (A/B testing; both give the same bits, the separate pass is slower). */
 #define MSDA_FLAG_DET_SEPARATE_FILL (1u << 14)
 #define MSDA_FLAG_FORCE_GENERIC (1u << 1) /* bypass the D in {16,32,64,128} fast kernels             */
-/* Row order = which rows a CTA works on.  A scheduling choice only: results never depend on it.  Without an order
- * flag the library picks (forward: LINEAR; backward: the folding encoder kernel when it applies, else STRIP). */
+/* Row order = which rows a CTA works on.  A scheduling choice only: results never depend on it.  The PRODUCT library
+ * carries one order per pass -- forward LINEAR, backward STRIP, the fastest pair on every measured configuration -- and
+ * treats the three flags below as hints it ignores; experiment builds (msda_build_config() & MSDA_BUILD_EXPERIMENTS) and
+ * the variant builds of tools/build_variant.sh instantiate all three orders for both passes and honour them. */
 #define MSDA_FLAG_ORDER_LINEAR (1u << 2)  /* rows in memory order (b, q, h)                              */
 /* One CTA = a strip of consecutive queries of ONE head (any Q): x-adjacent queries re-use corner lines in L1. */
 #define MSDA_FLAG_ORDER_STRIP (1u << 4)

@@ -106,6 +106,14 @@ int launch_bwd_fast(cudaStream_t st, const Dims& d, const void* go, const void* 
   } while (0)
 #endif
 
+// The product library instantiates ONE row order per pass -- LINEAR forward, STRIP backward, the pair that is fastest
+// on every measured config (profiles/r02t_sweep_row_orders.txt) -- and treats MSDA_FLAG_ORDER_* as hints it may
+// ignore (results never depend on the order).  Experiment builds (-DMSDA_EXPERIMENTS) and the slim variant builds
+// of tools/build_variant.sh carry all three orders for both passes.
+#if defined(MSDA_EXPERIMENTS) || defined(MSDA_EXP_SLIM)
+#define MSDA_ALL_ORDERS 1
+#endif
+
 // all three row orders (the plain operator)
 #define MSDA_ORDER_ANY(D_, VT_, PT_, CALL)                       \
   do {                                                           \

@@ -5,7 +5,12 @@ namespace msda_host {
 
 int fwd_fast(cudaStream_t st, const Dims& d, int dtype, unsigned flags, const void* value, const int64_t* shapes,
              const int64_t* lsi, const void* loc, const void* w, void* out) {
+#ifdef MSDA_ALL_ORDERS
 #define MSDA_DISPATCH_ORDER MSDA_ORDER_ANY
+#else
+#define MSDA_DISPATCH_ORDER MSDA_ORDER_LINEAR
+  (void)flags;
+#endif
 #define CALL_FWD(D_, VT_, PT_, ORD_) launch_fwd_fast<D_, VT_, PT_, kFwdThreads, ORD_>(st, d, value, shapes, lsi, loc, w, out)
   if (dtype == MSDA_F32) MSDA_DISPATCH_D(float, CALL_FWD);
   MSDA_DISPATCH_D(__nv_bfloat16, CALL_FWD);
