@@ -238,7 +238,7 @@ int msda_add_layernorm_backward(void* stream, const void* grad_y, const void* a,
  *   frac           [B*Q*H*L*P, 2] float  (lw, lh) fractional weights.
  * Same definition as msda_oracle_bookkeeping in oracle/msda_oracle.c; compared bit for bit.
  * On the shapes the fast kernels cover (float dispatch name "*_fast_*") the numbers are decoded from the very
- * record the fast kernels build per point (clamped low-corner offset + alias / validity flags), i.e. they are
+ * record the fast kernels build per point (unclamped low-corner offset + four corner-validity bits), i.e. they are
  * the addresses those kernels gather from and scatter to; elsewhere they come from the generic kernels'
  * coordinate code.
  */
