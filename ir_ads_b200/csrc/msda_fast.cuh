@@ -985,54 +985,6 @@ msda_bwd_fast_kernel(const VT* __restrict__ grad_out, const VT* __restrict__ val
     constexpr bool SCATTER = sizeof(ACC) != sizeof(NoScatter) && !EMIT;
     static_assert(!(sizeof(ACC) == 8 && CPL != 4), "the fixed-point red path transposes 4 channels per lane");
 
-#ifndef MSDA_BWD_MERGE
-#define MSDA_BWD_MERGE 0   // off until its GPU parity run is in (tools/gpu_r02z.sh)
-#endif
-    // Pre-reduction of the scatter inside a row.  The points of one level lie a pixel or two apart, so their 2 x 2
-    // footprints overlap: on model-like inputs 8 % (cfg 2) to 13 % (cfg 5) of a row's corners land on a pixel that an
-    // earlier point of the same row and level already scatters to.  Both contributions are weight x the SAME grad_out
-    // row, so they fold by adding the two scalar WEIGHTS -- no vector traffic: the later point hands its weight to the
-    // earliest point of the level that owns the pixel and issues no red for that corner.  Only the scatter weights
-    // (s_cw) change; the gather, the dot products and grad_sampling_loc / grad_attn_weight use the records' other
-    // fields.  (Float reds only: the fixed-point paths must form the same per-point contributions as msda_det.cuh.)
-    if constexpr (SCATTER && !DET && MSDA_BWD_MERGE != 0) {
-      if (cur.live) {
-        for (int pt = sub; pt < NP; pt += LANES) {
-          const int l = level_of<PT>(pt, P);
-          const int first = l * ((PT > 0) ? PT : P);
-          if (pt == first) continue;
-          const int oc = s_fin[pt].x;
-          if ((oc & 15) == 0) continue;                       // gated out / fully masked: nothing to hand over
-          const int dyl = tab->W[l] * HD;
-          // own weights: a component is either handed over (and zeroed) by this lane or added to by later points
-          // of the level, never both (a later point hands to the EARLIEST owner of the pixel), so component-wise
-          // stores and shared-memory atomics on the same record do not race
-          float4 cw = s_cw[pt];
-          float* mine_w = reinterpret_cast<float*>(&s_cw[pt]);
-          for (int q = first; q < pt; ++q) {
-            const int ocq = s_fin[q].x;
-            const int diff = (oc & ~15) - (ocq & ~15);          // own (x0, y0) corner relative to q's, in elements
-            if (abs(diff) > dyl + HD || (ocq & 15) == 0) continue;   // footprints apart (the common case)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {                       // own corner k: offset diff + e_k in q's frame
-              const float wk = (k == 0) ? cw.x : ((k == 1) ? cw.y : ((k == 2) ? cw.z : cw.w));
-              if (!(oc & (1 << k)) || wk == 0.0f) continue;
-              const int t = diff + ((k & 1) ? HD : 0) + ((k & 2) ? dyl : 0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if ((ocq & (1 << j)) && t == ((j & 1) ? HD : 0) + ((j & 2) ? dyl : 0)) {
-                  atomicAdd(reinterpret_cast<float*>(&s_cw[q]) + j, wk);   // rare; other lanes may hand over to q too
-                  mine_w[k] = 0.0f;
-                  if (k == 0) cw.x = 0.0f; else if (k == 1) cw.y = 0.0f; else if (k == 2) cw.z = 0.0f; else cw.w = 0.0f;
-                  break;
-                }
-              }
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
     const int64_t img = (int64_t)cur.b * S * HD + sub * CPL;
     const VT* vimg = value + img;
     ACC* gimg = grad_value + (DET ? img - sub * 3 : img);   // DET: lane offset is `sub`, not 4*sub

@@ -1,9 +1,10 @@
 #!/usr/bin/env bash
 # Round-2 GPU call Z: pre-reduction of the scatter inside a row (weights of corners that land on a pixel an earlier point of
-# the same row and level already scatters to are handed over; no red for them) -- whole suite, then A/B timing.
+# the same row and level already scatters to are handed over; no red for them) -- the whole suite against a FULL build with
+# -DMSDA_BWD_MERGE=1, then A/B timing of slim builds.
 set -u
 out=gpurun_out; mkdir -p "$out"; export PYTHONUNBUFFERED=1
-timeout 1200 python -u -m pytest tests -m gpu -x -q --timeout 300 --timeout-method=thread > "$out/pytest_r02z.log" 2>&1; echo "pytest exit $?" >> "$out/pytest_r02z.log"
+MSDA_B200_LIB=build/variants/lib_mergefull.so timeout 1200 python -u -m pytest tests -m gpu -x -q --timeout 300 --timeout-method=thread > "$out/pytest_r02z.log" 2>&1; echo "pytest exit $?" >> "$out/pytest_r02z.log"
 {
 for v in nomerge merge nomerge merge; do
   echo "== $v"
