@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--regions", type=int, default=3, help="timed regions of --steps steps each (median reported)")
     ap.add_argument("--no-graph", action="store_true", help="train mode: do not try CUDA-graph capture")
     ap.add_argument("--amp", action="store_true", help="train mode: bf16 autocast (AMP config)")
+    ap.add_argument("--tf32", action="store_true",
+                    help="train mode: TF32 tensor-core matmuls for the fp32 projections (torch 1.10, which the reference "
+                         "pins, enabled them by default; torch 2.x does not)")
     return ap.parse_args()
 
 
@@ -461,6 +464,8 @@ def run_train_mode(args, wl, dev, rank, world, dist_on):
 
     L = args.layers
     E = wl.num_heads * wl.head_dim
+    if args.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(0)                                    # identical initial weights on every rank (DDP broadcast)
     mods = torch.nn.ModuleList([MultiScaleDeformableAttention(E, wl.num_heads, wl.num_levels, wl.num_points, dropout=0.0,
                                                               batch_first=True) for _ in range(L)]).to(dev)
@@ -552,7 +557,8 @@ def run_train_mode(args, wl, dev, rank, world, dist_on):
             "metric": "msda_training_step_sampled_points_per_s", "value": pts / (ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "bf16 autocast (bf16 value, f32 accumulate)" if args.amp else "f32", "data": "synthetic",
+            "dtype": "bf16 autocast (bf16 value, f32 accumulate)" if args.amp else
+                     ("f32 (projections: TF32 tensor-core matmul)" if args.tf32 else "f32"), "data": "synthetic",
             "config": {"workload": f"{wl.name}: batch-sharded deformable-DETR training step -- {L} MSDeformAttn modules "
                                    "(projections + fused core op) fwd+bwd, per-module NCCL mean all-reduce of the "
                                    "projection-weight grads from gradient hooks, fused AdamW",
