@@ -34,8 +34,11 @@ int bwd_fast_noscatter(cudaStream_t st, const Dims& d, int dtype, const void* go
 // path: replaces det_bin_kernel<true> + the plain no-scatter backward), LINEAR order
 int bwd_fast_emit(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
                   const int64_t* lsi, const void* loc, const void* w, void* gl, void* gw, int* cursor,
-                  const int* bin_start, void* entries) {
-  msda::EmitArgs ea{cursor, bin_start, static_cast<int4*>(entries)};
+                  const int* bin_start, void* entries, float* warp_amax, int64_t* n_warps) {
+  // one CTA per kBwdThreads / (D / 4) rows (LINEAR order), kBwdThreads / 32 warps each: the slots of EmitArgs::warp_amax
+  const int64_t rpc = kBwdThreads / (d.D / 4);
+  if (n_warps) *n_warps = ((d.rows() + rpc - 1) / rpc) * (kBwdThreads / 32);
+  msda::EmitArgs ea{cursor, bin_start, static_cast<int4*>(entries), warp_amax};
 #define MSDA_DISPATCH_ORDER MSDA_ORDER_LINEAR
 #define CALL_BWD(D_, VT_, PT_, ORD_)                                                                            \
   launch_bwd_fast<D_, VT_, PT_, kBwdThreads, ORD_, msda::EmitEntries>(st, d, go, value, shapes, lsi, loc, w,   \

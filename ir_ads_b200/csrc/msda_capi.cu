@@ -180,7 +180,7 @@ struct DetLayout {
   int64_t bins;        // upper bound, B*H*(2S+2L)
   int64_t n_scan;      // bins + 1
   int64_t scan_blocks;
-  size_t off_cursor, off_sums, off_entries, off_misc, off_acc, total;
+  size_t off_cursor, off_sums, off_entries, off_misc, off_wamax, off_acc, total;
 };
 DetLayout det_layout(const Dims& d) {
   DetLayout l;
@@ -193,7 +193,9 @@ DetLayout det_layout(const Dims& d) {
   l.off_entries = l.off_sums + up((size_t)l.scan_blocks * 4);
   l.off_misc = l.off_entries + up((size_t)d.n_points() * 16);
   l.off_acc = l.off_misc + 256;
-  l.total = l.off_acc + (det_dense(d) ? up((size_t)d.n_value() * 8) : 0);   // accumulators: cell reduce only
+  l.off_wamax = l.off_acc + (det_dense(d) ? up((size_t)d.n_value() * 8) : 0);   // accumulators: cell reduce only
+  // two floats per warp of the entry-filing backward (<= 256 threads per CTA)
+  l.total = l.off_wamax + up((size_t)(d.rows() * d.D / 128 + 8) * 8);
   return l;
 }
 // the sorted path needs 32-bit bin / entry / row indices
@@ -403,17 +405,26 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
     } else {
       MSDA_CUDA(cudaMemsetAsync(workspace, 0, need, st));
     }
+    // The fixed-point scale comes from max |grad_out| x max |weight|.  On the sorted route the backward kernel that
+    // files the entries reads both tensors anyway and takes the two maxima itself (EmitArgs::amax); the scale is only
+    // needed by the reduction that follows it.  Every other route scatters with the scale and takes them up front.
+#ifndef MSDA_DET_AMAX_IN_EMIT
+#define MSDA_DET_AMAX_IN_EMIT 1
+#endif
+    const bool amax_in_emit = MSDA_DET_AMAX_IN_EMIT && sorted && !(flags & MSDA_FLAG_DET_SEPARATE_FILL);
     const int g_out = grid_for(n_out, 256, 148 * 8), g_pts = grid_for(n_pts, 256, 148 * 8);
-    if (dtype == MSDA_F32) msda::msda_amax_kernel<float><<<g_out, 256, 0, st>>>((const float*)grad_output, n_out, amax);
-    else if (dtype == MSDA_F64) msda::msda_amax_kernel<double><<<g_out, 256, 0, st>>>((const double*)grad_output, n_out, amax);
-    else msda::msda_amax_kernel<__nv_bfloat16><<<g_out, 256, 0, st>>>((const __nv_bfloat16*)grad_output, n_out, amax);
-    count();
-    if (dtype == MSDA_F64) msda::msda_amax_kernel<double><<<g_pts, 256, 0, st>>>((const double*)attn_weight, n_pts, amax + 1);
-    else msda::msda_amax_kernel<float><<<g_pts, 256, 0, st>>>((const float*)attn_weight, n_pts, amax + 1);
-    count();
-    msda::msda_det_scale_kernel<<<1, 1, 0, st>>>(amax, scale, dtype == MSDA_F64 ? 44 : 38);
-    count();
-    MSDA_CUDA(cudaGetLastError());
+    if (!amax_in_emit) {
+      if (dtype == MSDA_F32) msda::msda_amax_kernel<float><<<g_out, 256, 0, st>>>((const float*)grad_output, n_out, amax);
+      else if (dtype == MSDA_F64) msda::msda_amax_kernel<double><<<g_out, 256, 0, st>>>((const double*)grad_output, n_out, amax);
+      else msda::msda_amax_kernel<__nv_bfloat16><<<g_out, 256, 0, st>>>((const __nv_bfloat16*)grad_output, n_out, amax);
+      count();
+      if (dtype == MSDA_F64) msda::msda_amax_kernel<double><<<g_pts, 256, 0, st>>>((const double*)attn_weight, n_pts, amax + 1);
+      else msda::msda_amax_kernel<float><<<g_pts, 256, 0, st>>>((const float*)attn_weight, n_pts, amax + 1);
+      count();
+      msda::msda_det_scale_kernel<<<1, 1, 0, st>>>(amax, scale, dtype == MSDA_F64 ? 44 : 38);
+      count();
+      MSDA_CUDA(cudaGetLastError());
+    }
     if (sorted) {
       // sorted segment reduction (msda_det.cuh): count -> scan -> fill -> gather; no atomics on grad_value
       int* bins = reinterpret_cast<int*>(ws);
@@ -444,9 +455,25 @@ int msda_backward(void* stream, const void* grad_output, const void* value, cons
         if (int s2 = bwd_fast_noscatter(st, d, dtype, grad_output, value, spatial_shapes, level_start_index,
                                         sampling_loc, attn_weight, grad_sampling_loc, grad_attn_weight))
           return s2;
+      } else if (amax_in_emit) {
+        // the kernel leaves two maxima per warp; reducing those short arrays replaces the sweeps over grad_out / weights
+        float* wamax = reinterpret_cast<float*>(ws + lay.off_wamax);
+        int64_t n_warps = 0;
+        if (int s2 = bwd_fast_emit(st, d, dtype, grad_output, value, spatial_shapes, level_start_index, sampling_loc,
+                                   attn_weight, grad_sampling_loc, grad_attn_weight, cursor, bins, entries, wamax,
+                                   &n_warps))
+          return s2;
+        const int g_w = grid_for(n_warps, 256, 148 * 8);
+        msda::msda_amax_kernel<float><<<g_w, 256, 0, st>>>(wamax, n_warps, amax);
+        count();
+        msda::msda_amax_kernel<float><<<g_w, 256, 0, st>>>(wamax + n_warps, n_warps, amax + 1);
+        count();
+        msda::msda_det_scale_kernel<<<1, 1, 0, st>>>(amax, scale, 38);   // sorted route: float / bf16 only
+        count();
+        MSDA_CUDA(cudaGetLastError());
       } else if (int s2 = bwd_fast_emit(st, d, dtype, grad_output, value, spatial_shapes, level_start_index,
                                         sampling_loc, attn_weight, grad_sampling_loc, grad_attn_weight, cursor, bins,
-                                        entries)) {
+                                        entries, nullptr, nullptr)) {
         return s2;
       }
       if (!det_dense(d)) {

@@ -63,6 +63,29 @@ constexpr int kDetDenseRatio = 4;
 // upper bound of bins per (image, head) that needs only S and L: (H+1)(W+1) <= 2HW + 2
 __host__ __device__ constexpr int64_t det_cells_bound(int64_t S, int64_t L) { return 2 * S + 2 * L; }
 
+// Division of a 31-bit unsigned by a run-time constant as multiply-high + shift (Granlund-Montgomery, the round-up
+// form: m = ceil(2^(31+s) / d), s = ceil(log2 d), exact for n < 2^31).  The count pass below decomposes every
+// point index with four divisions; as `n / d` each costs an I2F + MUFU.RCP + F2I sequence on the quarter-rate
+// conversion pipe, and the pass is bound by its instruction issue.
+struct FastDiv {
+  unsigned m, s;   // d == 1: m == 0 (the quotient is n itself)
+};
+__device__ __forceinline__ FastDiv fastdiv_make(unsigned d) {
+  FastDiv f;
+  if (d <= 1u) {
+    f.m = 0u;
+    f.s = 0u;
+  } else {
+    const unsigned lg = 32u - (unsigned)__clz((int)(d - 1u));          // ceil(log2 d), d >= 2
+    f.m = (unsigned)(((1ull << (31u + lg)) + d - 1u) / d);
+    f.s = lg - 1u;
+  }
+  return f;
+}
+__device__ __forceinline__ unsigned fastdiv(unsigned n, const FastDiv f) {
+  return f.m ? (__umulhi(n, f.m) >> f.s) : n;
+}
+
 // FILL == false: count points per bin.  FILL == true: write entries (bins already scanned into `bin_start`).
 template <bool FILL>
 __global__ void __launch_bounds__(256)
@@ -70,18 +93,21 @@ det_bin_kernel(const float* __restrict__ loc, const float* __restrict__ w, const
                const int64_t* __restrict__ lsi, int H, int L, int Q, int P, int64_t n_points, int* __restrict__ counter,
                const int* __restrict__ bin_start, int4* __restrict__ entries) {
   __shared__ CellTab tab;
-  load_cell_tab(&tab, shapes, lsi, L);
+  __shared__ FastDiv div[4];   // by NP, P, H, Q
   const int NP = L * P;
+  if (threadIdx.x < 4) div[threadIdx.x] = fastdiv_make((unsigned)(threadIdx.x == 0 ? NP : (threadIdx.x == 1 ? P : (threadIdx.x == 2 ? H : Q))));
+  load_cell_tab(&tab, shapes, lsi, L);   // ends with a barrier
+  const FastDiv dNP = div[0], dP = div[1], dH = div[2], dQ = div[3];
   for (int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pt < n_points;
        pt += (int64_t)gridDim.x * blockDim.x) {
     // 32-bit index arithmetic: the sorted path is only taken when n_points < 2^31 (det_sorted_ok), and this kernel
-    // was bound by its 64-bit divisions (issue slots 79 % busy at cfg 5)
+    // was bound by its divisions (64-bit: issue slots 79 % busy at cfg 5; 32-bit `/`: 76 %)
     const unsigned p32 = (unsigned)pt;
-    const unsigned row = p32 / (unsigned)NP;
-    const int l = (int)((p32 - row * (unsigned)NP) / (unsigned)P);
-    const unsigned bq = row / (unsigned)H;
+    const unsigned row = fastdiv(p32, dNP);
+    const int l = (int)fastdiv(p32 - row * (unsigned)NP, dP);
+    const unsigned bq = fastdiv(row, dH);
     const int h = (int)(row - bq * (unsigned)H);
-    const int64_t b = bq / (unsigned)Q;
+    const int64_t b = fastdiv(bq, dQ);
     const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pt);
     const Cell<float> c = locate<float>(xy.x, xy.y, tab.H[l], tab.W[l]);
     if (c.valid == 0u) continue;
@@ -239,8 +265,18 @@ __device__ __forceinline__ float det_ld(const __nv_bfloat16* p) {
   return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
 }
 
+// No minimum-blocks bound on purpose: ptxas settles at 80 registers (3 CTAs per SM) and 2.09 ms at cfg 5; asking for
+// 4 CTAs (64 registers, 40 bytes of spills) gave 2.49 ms, and even a bound of 1 -- same register count, another
+// schedule -- 2.66 ms (profiles/r02af_det_variants.txt).  MSDA_DET_REDUCE_MINB > 0 is for variant builds.
+#ifndef MSDA_DET_REDUCE_MINB
+#define MSDA_DET_REDUCE_MINB 0
+#endif
 template <int D, typename VT>
+#if MSDA_DET_REDUCE_MINB > 0
+__global__ void __launch_bounds__(256, MSDA_DET_REDUCE_MINB)
+#else
 __global__ void __launch_bounds__(256)
+#endif
 det_cell_reduce_kernel(const VT* __restrict__ grad_out, const int4* __restrict__ entries,
                        const int* __restrict__ bin_start, int n_bins, const int64_t* __restrict__ shapes,
                        const int64_t* __restrict__ lsi, const DetScale* __restrict__ det,

@@ -83,7 +83,7 @@ int bwd_fast_noscatter(cudaStream_t st, const Dims& d, int dtype, const void* go
                        const int64_t* shapes, const int64_t* lsi, const void* loc, const void* w, void* gl, void* gw);
 int bwd_fast_emit(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
                   const int64_t* lsi, const void* loc, const void* w, void* gl, void* gw, int* cursor,
-                  const int* bin_start, void* entries);
+                  const int* bin_start, void* entries, float* warp_amax, int64_t* n_warps);
 int bwd_fused(cudaStream_t st, const Dims& d, int dtype, const void* go, const void* value, const int64_t* shapes,
               const int64_t* lsi, const void* off, const void* logits, float* gv, void* goff, void* glog,
               msda::FusedArgs fa);
