@@ -247,6 +247,10 @@ int msda_debug_bookkeeping(void* stream, const float* sampling_loc, const int64_
                            int num_heads, int channels, int num_levels, int num_query,
                            int num_point, int64_t* corner_offsets, float* frac);
 
+/* Test hook (host arithmetic only, no GPU): n / d as the deterministic path's count pass computes it -- multiply-high
+ * by a constant derived from d (csrc/msda_det.cuh, FastDiv).  Exact for n < 2^31 and 1 <= d < 2^31. */
+unsigned msda_debug_fastdiv(unsigned n, unsigned d);
+
 /* Human-readable name of a status code. */
 const char* msda_status_string(int status);
 /* Detail of the last failure on the calling thread ("" if none). */

@@ -78,6 +78,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_add_layernorm_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i, vp, vp, vp, vp, sz, i]
     lib.msda_debug_bookkeeping.restype = i
     lib.msda_debug_bookkeeping.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp, vp]
+    lib.msda_debug_fastdiv.restype = u
+    lib.msda_debug_fastdiv.argtypes = [u, u]
     lib.msda_status_string.restype = ctypes.c_char_p
     lib.msda_status_string.argtypes = [i]
     lib.msda_last_error_message.restype = ctypes.c_char_p

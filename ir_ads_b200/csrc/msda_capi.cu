@@ -260,6 +260,8 @@ unsigned msda_build_config(void) {
 
 uint64_t msda_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+unsigned msda_debug_fastdiv(unsigned n, unsigned d) { return msda::fastdiv(n, msda::fastdiv_make(d)); }
+
 const char* msda_last_error_message(void) { return g_err; }
 
 const char* msda_status_string(int status) {

@@ -70,20 +70,29 @@ __host__ __device__ constexpr int64_t det_cells_bound(int64_t S, int64_t L) { re
 struct FastDiv {
   unsigned m, s;   // d == 1: m == 0 (the quotient is n itself)
 };
-__device__ __forceinline__ FastDiv fastdiv_make(unsigned d) {
+// host + device (msda_debug_fastdiv in include/msda.h lets the CPU tests check the constants against `/`)
+__host__ __device__ __forceinline__ FastDiv fastdiv_make(unsigned d) {
   FastDiv f;
   if (d <= 1u) {
     f.m = 0u;
     f.s = 0u;
   } else {
+#ifdef __CUDA_ARCH__
     const unsigned lg = 32u - (unsigned)__clz((int)(d - 1u));          // ceil(log2 d), d >= 2
+#else
+    const unsigned lg = 32u - (unsigned)__builtin_clz(d - 1u);
+#endif
     f.m = (unsigned)(((1ull << (31u + lg)) + d - 1u) / d);
     f.s = lg - 1u;
   }
   return f;
 }
-__device__ __forceinline__ unsigned fastdiv(unsigned n, const FastDiv f) {
+__host__ __device__ __forceinline__ unsigned fastdiv(unsigned n, const FastDiv f) {
+#ifdef __CUDA_ARCH__
   return f.m ? (__umulhi(n, f.m) >> f.s) : n;
+#else
+  return f.m ? ((unsigned)(((unsigned long long)n * f.m) >> 32) >> f.s) : n;
+#endif
 }
 
 // FILL == false: count points per bin.  FILL == true: write entries (bins already scanned into `bin_start`).

@@ -210,3 +210,19 @@ int main(void) {
     assert res.returncode == 0, res.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0 and "c abi ok" in run.stdout, (run.returncode, run.stdout, run.stderr)
+
+
+def test_count_pass_division_constants_are_exact():
+    """The deterministic path's count pass divides point indices by L*P, P, H and Q with multiply-high constants
+    (csrc/msda_det.cuh, FastDiv) instead of `/`: the quotient must be exact for every n < 2^31.  Host arithmetic only."""
+    import random
+    h = _lib.lib()
+    rng = random.Random(7)
+    top = (1 << 31) - 1
+    divisors = [1, 2, 3, 4, 5, 7, 8, 16, 20, 40, 64, 100, 255, 256, 257, 300, 900, 2000, 17821, 21824, 22223, 65535, 65536,
+                65537, 1000003, 1 << 30, top] + [rng.randrange(1, 1 << 20) for _ in range(40)]
+    for d in divisors:
+        edge = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, top - 1, top, (top // d) * d, (top // d) * d - 1]
+        for n in edge + [rng.randrange(0, 1 << 31) for _ in range(200)]:
+            if 0 <= n <= top:
+                assert h.msda_debug_fastdiv(n, d) == n // d, (n, d)
