@@ -40,7 +40,7 @@
 // -DMSDA_DEBUG_BOUNDS (variant builds only, tools/build_variant.sh): every corner offset that is about to be
 // dereferenced -- gather, scatter, padding-mask byte -- is checked against the image; a violation prints and traps.
 // The records hold UNCLAMPED offsets whose validity bits alone keep the loops inside the map, and compute-sanitizer
-// is not available on the GPU pool, so this is the memcheck of the parity suite (tools/gpu_r02n.sh).
+// is not available on the GPU pool, so this is the memcheck of the parity suite (tools/gpu_calls/gpu_r02n.sh).
 #ifdef MSDA_DEBUG_BOUNDS
 #include <cstdio>
 #define MSDA_CHECK_OFFSET(off, limit, what)                                                                  \

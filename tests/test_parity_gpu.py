@@ -164,7 +164,7 @@ def test_row_orders_agree(D, P, dtype):
     the same forward and the same grad_loc / grad_w as the LINEAR order bit for bit (same per-row arithmetic) and
     the same grad_value up to float summation order.  (The product library carries one order per pass and ignores
     the order hints, so there the comparison is trivially true; the experiment build -- the second pytest command of
-    tools/gpu_r02*.sh -- instantiates and honours all of them.)"""
+    tools/gpu_calls/gpu_r02*.sh -- instantiates and honours all of them.)"""
     _, _lib, _, workloads, msda_c, _ = _mods()
     levels = [(21, 37), (11, 19), (6, 10), (3, 5)]
     value, shapes, lsi, loc, w = workloads.make_inputs(levels, 2, 0, 4, D, P, "encoder", "model", 3, value_dtype=dtype)

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Round-2 GPU call M: compute-sanitizer memcheck over the parity tests that exercise padded / gated / masked corners
-# (compute-sanitizer turned out to be closed on this GPU pool; tools/gpu_r02n.sh -- the -DMSDA_DEBUG_BOUNDS build -- replaced it)
+# (compute-sanitizer turned out to be closed on this GPU pool; tools/gpu_calls/gpu_r02n.sh -- the -DMSDA_DEBUG_BOUNDS build -- replaced it)
 # (the records hold UNCLAMPED offsets now: prove that no corner outside the map is ever dereferenced).
 set -u
 out=gpurun_out; mkdir -p "$out"; export PYTHONUNBUFFERED=1
