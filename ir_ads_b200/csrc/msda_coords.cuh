@@ -26,12 +26,35 @@ struct DetScale {
   float inv_scale;  // 2^-k (NaN when the inputs were not finite)
 };
 
-// One fixed-point contribution is round((w * scale) * g): the corner weight w (bilinear weight x attention weight)
+// One fixed-point contribution is round((w * scale) * g) -- det_contrib below: the corner weight w (bilinear weight x attention weight)
 // is scaled first -- scale is a power of two, so that product is exact -- which leaves ONE multiplication per
 // channel.  The three deterministic paths of the fast shapes (fixed-point reds in msda_fast.cuh, per-pixel gather and
 // cell reduce in msda_det.cuh) form their contributions with exactly this expression, which is what makes their
 // results bit-identical.  (The product only differs from (w * g) * scale when w * g is subnormal.)
 __device__ __forceinline__ float det_weight(float w, float scale) { return __fmul_rn(w, scale); }
+
+// The contribution itself, det_contrib(w * scale, g), as a 64-bit integer.
+//   MSDA_DET_FP64 = 1 (default): the round-to-nearest-even integer of the EXACT product.  Both factors are floats, so
+//     their product has at most 48 significant bits and is exact in double; ONE fused multiply-add with the addend
+//     1.5 * 2^52 rounds it to an integer and leaves that integer in the low mantissa bits (|product| <= 2^38 by the
+//     choice of the scale, far inside the trick's 2^51).  One rounding instead of two, and per entry of the cell reduce
+//     8 F2F.F64.F32 + 16 DFMA instead of 16 FMUL + 16 F2I.S64: every float conversion issues at 16 lanes per clock and
+//     SM on B200, DFMA at 64 (profiles/r02ak_cvt_rates.txt).  Measured: cfg 5 backward 4.70 -> 4.67 ms, the sparse
+//     decoder problem 0.603 -> 0.587 ms -- halving the conversion-pipe cycles barely moves the cell reduce, so that pipe
+//     was not what bound it (profiles/r02af_det_variants.txt, item 5).
+//   MSDA_DET_FP64 = 0 (variant builds): the round-2 definition, the float product rounded once more to an integer.
+#ifndef MSDA_DET_FP64
+#define MSDA_DET_FP64 1
+#endif
+#if MSDA_DET_FP64
+using det_factor = double;
+__device__ __forceinline__ long long det_contrib(double ws, double g) {
+  return __double_as_longlong(__fma_rn(ws, g, 6755399441055744.0)) - 0x4338000000000000LL;   // 1.5 * 2^52 and its bits
+}
+#else
+using det_factor = float;
+__device__ __forceinline__ long long det_contrib(float ws, float g) { return __float2ll_rn(ws * g); }
+#endif
 
 template <typename T>
 struct AxisSplit {

@@ -241,12 +241,13 @@ det_gather_kernel(const VT* __restrict__ grad_out, const int4* __restrict__ entr
         const int4 ent = __ldg(entries + e);
         const float lw = __int_as_float(ent.y), lh = __int_as_float(ent.z), aw = __int_as_float(ent.w);
         const float hh = 1.0f - lh, hw = 1.0f - lw;
-        const float c = det_weight((k == 0 ? hh * hw : (k == 1 ? hh * lw : (k == 2 ? lh * hw : lh * lw))) * aw, scale);
+        const det_factor c =
+            (det_factor)det_weight((k == 0 ? hh * hw : (k == 1 ? hh * lw : (k == 2 ? lh * hw : lh * lw))) * aw, scale);
         const float4 go = ld4(grad_out + (int64_t)ent.x * D + sub * 4);
-        a0 += __float2ll_rn(c * go.x);
-        a1 += __float2ll_rn(c * go.y);
-        a2 += __float2ll_rn(c * go.z);
-        a3 += __float2ll_rn(c * go.w);
+        a0 += det_contrib(c, (det_factor)go.x);
+        a1 += det_contrib(c, (det_factor)go.y);
+        a2 += det_contrib(c, (det_factor)go.z);
+        a3 += det_contrib(c, (det_factor)go.w);
       }
     }
   }
@@ -370,12 +371,13 @@ det_cell_reduce_kernel(const VT* __restrict__ grad_out, const int4* __restrict__
     }
     const float lw = __int_as_float(ent.y), lh = __int_as_float(ent.z), aw = __int_as_float(ent.w);
     const float hh = 1.0f - lh, hw = 1.0f - lw;
-    const float c[4] = {det_weight(hh * hw * aw, scale), det_weight(hh * lw * aw, scale),
-                        det_weight(lh * hw * aw, scale), det_weight(lh * lw * aw, scale)};
+    const det_factor c[4] = {(det_factor)det_weight(hh * hw * aw, scale), (det_factor)det_weight(hh * lw * aw, scale),
+                             (det_factor)det_weight(lh * hw * aw, scale), (det_factor)det_weight(lh * lw * aw, scale)};
+    const det_factor gd[4] = {(det_factor)g[0], (det_factor)g[1], (det_factor)g[2], (det_factor)g[3]};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[k][i] += __float2ll_rn(c[k] * g[i]);
+      for (int i = 0; i < 4; ++i) a[k][i] += det_contrib(c[k], gd[i]);
     ent = ent1;
     ent1 = ent2;
 #pragma unroll

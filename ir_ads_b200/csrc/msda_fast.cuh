@@ -801,13 +801,13 @@ __device__ __forceinline__ Vec<N> load_scatter_layout(const VT* row, int sub, co
 // instead of four partial ones (there is no vector form of the 64-bit integer red).
 template <int LANES>
 __device__ __forceinline__ void scatter4_det(unsigned long long* g, const float c, const float4 go, float scale) {
-  // the weight is scaled by the power of two first (exact), the product with grad_out is rounded to float, then to
-  // an integer: det_weight (msda_coords.cuh) is shared with msda_det.cuh so that all three paths give the same bits
-  const float cs = det_weight(c, scale);
-  atomicAdd(g + 0 * LANES, (unsigned long long)__float2ll_rn(cs * go.x));
-  atomicAdd(g + 1 * LANES, (unsigned long long)__float2ll_rn(cs * go.y));
-  atomicAdd(g + 2 * LANES, (unsigned long long)__float2ll_rn(cs * go.z));
-  atomicAdd(g + 3 * LANES, (unsigned long long)__float2ll_rn(cs * go.w));
+  // the weight is scaled by the power of two first (exact), then its product with grad_out is rounded to an integer:
+  // det_weight / det_contrib (msda_coords.cuh) are shared with msda_det.cuh so that all three paths give the same bits
+  const det_factor cs = (det_factor)det_weight(c, scale);
+  atomicAdd(g + 0 * LANES, (unsigned long long)det_contrib(cs, (det_factor)go.x));
+  atomicAdd(g + 1 * LANES, (unsigned long long)det_contrib(cs, (det_factor)go.y));
+  atomicAdd(g + 2 * LANES, (unsigned long long)det_contrib(cs, (det_factor)go.z));
+  atomicAdd(g + 3 * LANES, (unsigned long long)det_contrib(cs, (det_factor)go.w));
 }
 
 // lane `sub` owns channels 4*sub..4*sub+3 in v; returns channels {sub, LANES+sub, 2*LANES+sub, 3*LANES+sub}
