@@ -226,3 +226,24 @@ def test_count_pass_division_constants_are_exact():
         for n in edge + [rng.randrange(0, 1 << 31) for _ in range(200)]:
             if 0 <= n <= top:
                 assert h.msda_debug_fastdiv(n, d) == n // d, (n, d)
+
+
+def test_backward_workspace_sizes():
+    """Host logic of msda_backward_workspace_bytes (no GPU work): nothing for the float path, float accumulators for
+    bf16, and for the deterministic sorted path room for the 16-byte entries, the bin tables, the per-warp maxima of the
+    entry-filing backward (two floats per warp) and -- dense problems only -- the 64-bit accumulators."""
+    h = _lib.lib()
+    B, S, H, D, L, Q, P = 8, 22223, 8, 32, 4, 22223, 4
+    n_value, n_pts, rows = B * S * H * D, B * Q * H * L * P, B * Q * H
+    assert h.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, _lib.MSDA_F32, 0) == 0
+    assert h.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, _lib.MSDA_BF16, 0) == n_value * 4
+    det = h.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, _lib.MSDA_F32, _lib.FLAG_DETERMINISTIC)
+    warps = rows * D // 128
+    assert det >= n_pts * 16 + n_value * 8 + warps * 8 and det % 256 == 0          # dense: encoder self-attention
+    sparse = h.msda_backward_workspace_bytes(B, S, H, D, L, 300, P, _lib.MSDA_F32, _lib.FLAG_DETERMINISTIC)
+    assert B * 300 * H * L * P * 16 <= sparse < n_value * 8                         # sparse: no accumulators
+    atomic = h.msda_backward_workspace_bytes(B, S, H, D, L, Q, P, _lib.MSDA_F32,
+                                             _lib.FLAG_DETERMINISTIC | _lib.FLAG_DET_ATOMIC)
+    assert atomic == n_value * 8 + 64                                              # fixed-point reds: accumulators only
+    generic = h.msda_backward_workspace_bytes(B, S, H, 30, L, Q, P, _lib.MSDA_F32, _lib.FLAG_DETERMINISTIC)
+    assert generic == B * S * H * 30 * 8 + 64
